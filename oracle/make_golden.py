@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""
+TEST INFRASTRUCTURE.  Generates the committed golden vectors under tests/golden/ by running
+the REFERENCE ITSELF (oracle/_ref = mechanical py3 transliteration built by
+oracle/build_ref.py from /root/reference) on seeded synthetic inputs, together with the two
+flavours of the restated oracle (oracle/lm_oracle.py faithful / clean) so that the robust set
+ is stored next to the reference answers.
+
+Run in the build container (needs /root/reference):
+    python oracle/make_golden.py [--procs 8]
+
+Outputs (all small .npz):
+  tests/golden/kat1_fit.npz              SURVEY.md App. D KAT-1
+  tests/golden/detect_<name>.npz         candidate lists + thresholds for several frames/params
+  tests/golden/fits5_seed0.npz           every candidate of the config-1 frame (seed 0):
+                                         reference params/status/niter/nfev/fnorm/perror,
+                                         oracle n_qrsolv / n_reject, clean-oracle params/status/fnorm,
+                                         metrics (r_2, rmse, s_n), final PSF keys after consolidation
+  tests/golden/fits11_seed0.npz          200 windows 11x11, default gaussfit arguments
+"""
+import argparse
+import hashlib
+import multiprocessing
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref                                  # noqa: E402
+from oracle import pflib_oracle as po                         # noqa: E402
+from fluorosequencingimageanalysis_b200 import synth          # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+_REF = None
+
+
+def ref():
+    global _REF
+    if _REF is None:
+        build_ref.build(quiet=True)
+        _REF = build_ref.load()
+    return _REF
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------ per-window workers
+def _fit5(sub):
+    pflib, gaussfitter, _ = ref()
+    p, lmin, lmax, mn, mx = po.pflib_fit_args(sub)
+    mp = gaussfitter.gaussfit(sub, params=p, limitedmin=lmin, limitedmax=lmax, minpars=mn,
+                              maxpars=mx, returnmp=True)
+    fa, fit_fa = po.gaussfit(sub, params=p, limitedmin=lmin, limitedmax=lmax, minpars=mn,
+                             maxpars=mx, faithful=True)
+    cl, fit_cl = po.gaussfit(sub, params=p, limitedmin=lmin, limitedmax=lmax, minpars=mn,
+                             maxpars=mx, faithful=False)
+    same = (np.array_equal(mp.params, fa.params) and mp.status == fa.status and
+            mp.niter == fa.niter and mp.nfev == fa.nfev and mp.fnorm == fa.fnorm)
+    fitimg = gaussfitter.twodgaussian(mp.params, 0, 1, 1)(*np.indices(sub.shape))
+    r_2, rmse, s_n = po.fit_metrics(sub, fitimg)
+    perr = mp.perror if mp.perror is not None else np.full(7, np.nan)
+    return (mp.params, perr, mp.status, mp.niter, mp.nfev, mp.fnorm, fa.n_qrsolv, fa.n_reject,
+            cl.params, cl.status, cl.niter, cl.nfev, cl.fnorm, cl.n_qrsolv, same, r_2, rmse, s_n)
+
+
+def _fit11(win):
+    pflib, gaussfitter, _ = ref()
+    mp = gaussfitter.gaussfit(win, returnmp=True)
+    fa, _ = po.gaussfit(win, faithful=True)
+    cl, _ = po.gaussfit(win, faithful=False)
+    same = (np.array_equal(mp.params, fa.params) and mp.status == fa.status and
+            mp.niter == fa.niter and mp.nfev == fa.nfev and mp.fnorm == fa.fnorm)
+    perr = mp.perror if mp.perror is not None else np.full(7, np.nan)
+    p0 = np.array(po.moments(win), dtype=float)
+    return (mp.params, perr, mp.status, mp.niter, mp.nfev, mp.fnorm, fa.n_qrsolv, fa.n_reject,
+            cl.params, cl.status, cl.niter, cl.nfev, cl.fnorm, same, p0)
+
+
+def _stack(rows, names):
+    out = {}
+    for i, n in enumerate(names):
+        out[n] = np.array([r[i] for r in rows])
+    return out
+
+
+# ------------------------------------------------------------------ generators
+def make_kat1():
+    pflib, gaussfitter, _ = ref()
+    r, c = np.indices((5, 5))
+    sub = np.random.default_rng(0).poisson(
+        100 + 2000 * np.exp(-((r - 2.3) ** 2 + (c - 2.7) ** 2) / (2 * 1.1 ** 2))).astype(np.int64)
+    out = pflib._fit_2d_gaussian(sub)
+    p, lmin, lmax, mn, mx = po.pflib_fit_args(sub)
+    mp = gaussfitter.gaussfit(sub, params=p, limitedmin=lmin, limitedmax=lmax, minpars=mn,
+                              maxpars=mx, returnmp=True)
+    np.savez(os.path.join(GOLD, "kat1_fit.npz"), sub=sub,
+             fit7=np.array([float(v) for v in out[:7]]), fit_img=out[7],
+             status=mp.status, niter=mp.niter, nfev=mp.nfev, fnorm=mp.fnorm, perror=mp.perror,
+             covar=mp.covar, s_n=pflib.illumina_s_n(sub))
+    print("kat1", out[:7], mp.status, mp.niter, mp.nfev, mp.fnorm)
+
+
+def make_detect():
+    pflib, _, _ = ref()
+    cases = {
+        "c1_seed0": dict(img=synth.synth_frame(0), kw={}),
+        "c1_seed3": dict(img=synth.synth_frame(3), kw={}),
+        "dense_1000": dict(img=synth.synth_frame(11, n_spots=1000), kw={}),
+        "rect_200x333": dict(img=synth.synth_frame(5, H=200, W=333, n_spots=120), kw={}),
+        "cstd3_mf7": dict(img=synth.synth_frame(7, H=256, W=256, n_spots=150),
+                          kw=dict(median_filter_size=7, c_std=3)),
+        "mf3": dict(img=synth.synth_frame(8, H=128, W=160, n_spots=60),
+                    kw=dict(median_filter_size=3)),
+        "k3x3": dict(img=synth.synth_frame(9, H=128, W=128, n_spots=50),
+                     kw=dict(correlation_matrix=np.array([[-1, -1, -1], [-1, 8, -1], [-1, -1, -1]]))),
+        "k7x7": dict(img=synth.synth_frame(10, H=96, W=120, n_spots=40),
+                     kw=dict(correlation_matrix=(np.arange(49).reshape(7, 7) % 5 - 2) * 100 +
+                             np.pad(np.full((3, 3), 900), 2))),
+        "full16bit": dict(img=(np.random.default_rng(21).integers(0, 65536, (96, 96))
+                               .astype(np.uint16)), kw={}),
+        "flat": dict(img=np.full((64, 64), 400, dtype=np.uint16), kw={}),
+        "tiny_6x7": dict(img=synth.synth_frame(2, H=24, W=24, n_spots=2)[:6, :7].copy(), kw={}),
+    }
+    for name, c in cases.items():
+        img = c["img"]
+        cands = pflib._psf_candidates(img, **c["kw"])
+        _, cm, thr = po.detect_maps(img, **c["kw"])
+        assert cands == po.psf_candidates(img, **c["kw"]), name
+        kw = {("kw_" + k): np.asarray(v) for k, v in c["kw"].items()}
+        np.savez_compressed(os.path.join(GOLD, "detect_%s.npz" % name), img=img,
+                            cands=np.array(cands, dtype=np.int32).reshape(-1, 2), thr=thr,
+                            cm_sum=np.int64(cm.sum()), cm_max=np.int64(cm.max()), **kw)
+        print("detect", name, img.shape, len(cands), repr(float(thr)))
+
+
+def make_fits5(procs):
+    pflib, _, _ = ref()
+    img = synth.synth_frame(0)
+    cands = pflib._psf_candidates(img)
+    subs = [img[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in cands]
+    t = time.time()
+    with multiprocessing.Pool(procs) as pool:
+        rows = pool.map(_fit5, subs, chunksize=16)
+    dt = time.time() - t
+    names = ["ref_params", "ref_perror", "ref_status", "ref_niter", "ref_nfev", "ref_fnorm",
+             "n_qrsolv", "n_reject", "clean_params", "clean_status", "clean_niter", "clean_nfev",
+             "clean_fnorm", "clean_n_qrsolv", "oracle_equals_ref", "r_2", "rmse", "s_n"]
+    d = _stack(rows, names)
+    # the reference's full pipeline on the same frame (consolidation + re-key) -- one more
+    # pass would cost 500 s, so rebuild it from the per-candidate reference answers with the
+    # restated consolidation (checked equal to the reference's on a sub-frame below)
+    bins = {}
+    for (h, w), row in zip(cands, rows):
+        p = row[0]
+        if row[15] < 0.7:
+            continue
+        bins[(h, w)] = (p[2] + h - 2.5, p[3] + w - 2.5, p[0], p[1], p[4], p[5], p[6], None, None,
+                        row[16], row[15], row[17])
+    final = po.consolidate(bins, img.shape, 4)
+    keys = np.array(sorted(final.keys()), dtype=np.int32).reshape(-1, 2)
+    np.savez_compressed(os.path.join(GOLD, "fits5_seed0.npz"), img_sha=sha(img),
+                        cands=np.array(cands, dtype=np.int32), final_keys=keys,
+                        final_h0=np.array([final[tuple(k)][0] for k in keys]),
+                        final_w0=np.array([final[tuple(k)][1] for k in keys]),
+                        ref_seconds_total=dt, procs=procs, **d)
+    st, cnt = np.unique(d["ref_status"], return_counts=True)
+    print("fits5: %d fits in %.1f s on %d procs; status %s; oracle==ref %d/%d; robust(n_qrsolv==0) %d; "
+          "accepted %d; final %d" % (len(rows), dt, procs, dict(zip(st.tolist(), cnt.tolist())),
+                                     int(d["oracle_equals_ref"].sum()), len(rows),
+                                     int((d["n_qrsolv"] == 0).sum()), len(bins), len(final)))
+
+
+def make_pipeline_small():
+    """Reference find_peptides end to end on a small crop (bounded cost) -- pins consolidation."""
+    pflib, _, _ = ref()
+    img = synth.synth_frame(4, H=96, W=96, n_spots=30)
+    t = time.time()
+    out = pflib.find_peptides(img)
+    dt = time.time() - t
+    mine = po.find_peptides(img, faithful=True)
+    assert sorted(out.keys()) == sorted(mine.keys())
+    for k in out:
+        for a, b in zip(out[k], mine[k]):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), k
+    keys = np.array(sorted(out.keys()), dtype=np.int32).reshape(-1, 2)
+    vals = np.array([[float(v) for v in out[tuple(k)][:7]] + [float(out[tuple(k)][i]) for i in (9, 10, 11)]
+                     for k in keys])
+    np.savez_compressed(os.path.join(GOLD, "pipeline_small.npz"), img=img, keys=keys, vals=vals,
+                        sub_imgs=np.array([out[tuple(k)][7] for k in keys]),
+                        fit_imgs=np.array([out[tuple(k)][8] for k in keys]))
+    print("pipeline_small: %d psfs in %.1f s; oracle find_peptides identical" % (len(keys), dt))
+
+
+def make_fits11(procs):
+    img, cr, cc, amp = synth.synth_frame_with_truth(0)
+    wins = synth.cut_windows(img, cr, cc, 11)[:200]
+    with multiprocessing.Pool(procs) as pool:
+        rows = pool.map(_fit11, list(wins), chunksize=8)
+    names = ["ref_params", "ref_perror", "ref_status", "ref_niter", "ref_nfev", "ref_fnorm",
+             "n_qrsolv", "n_reject", "clean_params", "clean_status", "clean_niter", "clean_nfev",
+             "clean_fnorm", "oracle_equals_ref", "p0"]
+    d = _stack(rows, names)
+    np.savez_compressed(os.path.join(GOLD, "fits11_seed0.npz"), windows=wins, **d)
+    st, cnt = np.unique(d["ref_status"], return_counts=True)
+    print("fits11: %d; status %s; oracle==ref %d; robust %d" % (
+        len(rows), dict(zip(st.tolist(), cnt.tolist())), int(d["oracle_equals_ref"].sum()),
+        int((d["n_qrsolv"] == 0).sum())))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    todo = a.only.split(",") if a.only else ["kat1", "detect", "pipeline_small", "fits11", "fits5"]
+    if "kat1" in todo:
+        make_kat1()
+    if "detect" in todo:
+        make_detect()
+    if "pipeline_small" in todo:
+        make_pipeline_small()
+    if "fits11" in todo:
+        make_fits11(a.procs)
+    if "fits5" in todo:
+        make_fits5(a.procs)
