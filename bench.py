@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the spot hot path (BASELINE.json metric: 2-D Gaussian PSF
+candidate fits/s and frames/s) on N B200s of one node, with the reference CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- a 40-frame stack of one 512x512 field,
+~500 spots, every frame through detection + per-candidate 5x5 fit + metrics (what
+basic_image_script would do on that directory).  One "step" = one pass over one 40-frame stack.
+A pool of 8 different stacks (168 MB > 126 MB L2) is cycled so no step re-reads inputs that are
+still L2-resident.  N > 1: every rank runs its own stacks (weak scaling, no collective).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_FRAMES, H, W, N_SPOTS = 40, 512, 512, 500
+N_VARIANTS = 8
+# SURVEY.md 8(d) FLOP convention, `minpack` mode, per executed LM iteration, P = 25, n = 7:
+# 8 evaluations (176 P) + Householder QR (2 P n^2 - 2/3 n^3 = 2221) + Q^T f (4 P n = 700) + lmpar (~10 x 350)
+FLOP_PER_LM_ITER_5x5 = 176 * 25 + 2221 + 700 + 3500
+METRIC = "2-D Gaussian PSF candidate fits/s (detection + 5x5 LM fit + metrics), frames/s alongside"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_stack(seed):
+    from fluorosequencingimageanalysis_b200 import synth
+    return synth.synth_timetrace(seed, n_frames=N_FRAMES, H=H, W=W, n_spots=N_SPOTS)
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def _ref_worker_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    global _REF_FIT
+    _REF_FIT = None
+
+
+def _ref_fit_one(sub):
+    """One candidate through the reference's pflib._fit_2d_gaussian + metrics (oracle/_ref when
+    built, else the restated oracle port)."""
+    global _REF_FIT
+    if _REF_FIT is None:
+        from oracle import build_ref, pflib_oracle as po
+        mods = build_ref.load()
+        if mods is not None:
+            pf = mods[0]
+
+            def fit(s):
+                out = pf._fit_2d_gaussian(s)
+                fit_img = out[7]
+                r_2 = 1.0 - sum(np.reshape((s - fit_img) ** 2, -1)) / sum((np.reshape(s, -1) - np.mean(s)) ** 2)
+                return r_2, pf.illumina_s_n(s)
+            _REF_FIT = ("reference", fit)
+        else:
+            def fit(s):
+                out = po.fit_2d_gaussian(s, faithful=True)
+                return po.fit_metrics(s, out[7])[0], po.illumina_s_n(s)
+            _REF_FIT = ("port", fit)
+    return _REF_FIT[1](sub)
+
+
+def _ref_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.load() is not None else "port"
+
+
+def _ref_detect(img):
+    from oracle import build_ref, pflib_oracle as po
+    mods = build_ref.load()
+    if mods is not None:
+        return mods[0]._psf_candidates(img)
+    return po.psf_candidates(img)
+
+
+def cpu_reference_sample(frames, n_fits, cores, pool=None):
+    """Times the reference CPU path on a bounded sample of the workload: detection on full frames
+    (2 frames) and `n_fits` candidate fits fanned out over `cores` processes exactly like
+    pflib.parallel_image_batch's Pool (pflib.py:1082).  Returns dict(fits_per_s, frames_per_s, ...)."""
+    import multiprocessing
+    t0 = time.perf_counter()
+    cands = _ref_detect(frames[0])
+    t_det = time.perf_counter() - t0
+    rng = np.random.default_rng(12345)
+    pick = rng.choice(len(cands), size=min(n_fits, len(cands)), replace=False)
+    subs = [frames[0][cands[i][0] - 2:cands[i][0] + 3, cands[i][1] - 2:cands[i][1] + 3].astype(np.int64) for i in pick]
+    own = pool is None
+    if own:
+        pool = multiprocessing.Pool(cores, initializer=_ref_worker_init)
+        pool.map(_ref_fit_one, subs[:cores])           # import / warm the workers
+    t0 = time.perf_counter()
+    pool.map(_ref_fit_one, subs, chunksize=max(1, len(subs) // (cores * 4)))
+    t_fit = time.perf_counter() - t0
+    if own:
+        pool.close()
+        pool.join()
+    fits_per_s = len(subs) / t_fit
+    frames_per_s = 1.0 / (t_det / 1.0 / cores + len(cands) / fits_per_s)   # detection also fans out over files
+    return dict(fits_per_s=fits_per_s, frames_per_s=frames_per_s, n_fits=len(subs), t_fit=t_fit,
+                t_detect_per_frame=t_det, cands_per_frame=len(cands))
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on this box's host cores."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import multiprocessing
+    cores = os.cpu_count() or 1
+    frames = make_stack(7000)[:1]
+    kind = _ref_kind()
+    per_step = max(cores * 24, 64)                    # ~2.5 s of CPU work per step at ~0.1 s/fit/core
+    pool = multiprocessing.Pool(cores, initializer=_ref_worker_init)
+    cands = _ref_detect(frames[0])
+    rng = np.random.default_rng(999)
+    steps = args.warmup + args.steps
+    times, nf = [], []
+    for s in range(steps):
+        pick = rng.choice(len(cands), size=min(per_step, len(cands)), replace=False)
+        subs = [frames[0][cands[i][0] - 2:cands[i][0] + 3, cands[i][1] - 2:cands[i][1] + 3].astype(np.int64) for i in pick]
+        t0 = time.perf_counter()
+        pool.map(_ref_fit_one, subs, chunksize=max(1, len(subs) // (cores * 4)))
+        times.append(time.perf_counter() - t0)
+        nf.append(len(subs))
+    pool.close()
+    pool.join()
+    t = sum(times[args.warmup:])
+    n = sum(nf[args.warmup:])
+    value = n / t
+    t0 = time.perf_counter()
+    _ref_detect(frames[0])
+    t_det = time.perf_counter() - t0
+    sample = "%d candidate fits per step (random candidates of one 512x512 frame of the workload) on %d processes; detection timed on 1 full frame" % (per_step, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots, every frame fitted",
+                   "reference_sample": sample},
+        "frames_per_s": 1.0 / (t_det / cores + len(cands) / value),
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fluorosequencingimageanalysis_b200 import engine, _lib
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = _lib.load()
+    # ---- synthetic inputs: N_VARIANTS different 40-frame stacks, host (pinned) and device copies
+    stacks_host = []
+    for v in range(N_VARIANTS):
+        st = make_stack(1 + 100 * rank + v)
+        t = torch.from_numpy(st.view(np.int16)).view(torch.uint16).pin_memory()
+        stacks_host.append(t)
+    stacks_dev = [t.to(dev) for t in stacks_host]
+    pipe = engine.FieldPipeline(N_FRAMES, H, W, dtype=torch.uint16, faithful=not args.clean)
+    pinned = pipe.pinned_buffers()
+    in_bytes = N_FRAMES * H * W * 2
+
+    # ---- warm-up
+    for w in range(max(args.warmup, 3)):
+        pipe.run(stacks_dev[w % N_VARIANTS])
+    torch.cuda.synchronize()
+    n_probe = pipe.total()
+
+    # ---- timed region A: inputs resident in HBM, K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    totals = torch.zeros(args.steps, dtype=torch.int64, device=dev)
+    niters = torch.zeros(args.steps, dtype=torch.int64, device=dev)
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        pipe.run(stacks_dev[(k + 3) % N_VARIANTS])
+        totals[k] = pipe.n_cand[pipe.F]                       # device-side bookkeeping, no sync
+    ev[1].record()
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop()
+    fits_total = int(totals.sum().item())
+    if int(totals.max().item()) > pipe.cap:
+        raise RuntimeError("candidate capacity exceeded")
+
+    # ---- fit kernel alone (roofline): K launches re-fitting the last detection, events per launch
+    fit_ms = []
+    for k in range(max(3, min(args.steps, 8))):
+        frames_k = stacks_dev[(args.steps - 1 + 3) % N_VARIANTS]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.run_fit_only(frames_k)
+        e1.record()
+        e1.synchronize()
+        fit_ms.append(e0.elapsed_time(e1))
+    n_last = pipe.total()
+    sum_niter = int(pipe.out_int[:n_last, engine.ICOL_NITER].sum().item())
+    sum_nfev = int(pipe.out_int[:n_last, engine.ICOL_NFEV].sum().item())
+    fit_ms_avg = float(np.mean(fit_ms[1:])) if len(fit_ms) > 1 else float(fit_ms[0])
+    # detection alone
+    det_ms = []
+    for k in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.run_detect_only(stacks_dev[(k + 5) % N_VARIANTS])
+        e1.record()
+        e1.synchronize()
+        det_ms.append(e0.elapsed_time(e1))
+    det_ms_avg = float(np.mean(det_ms[1:]))
+
+    # ---- timed region B (e2e): host pinned frames in, packed results back on the host, every step
+    for w in range(2):
+        d = stacks_host[w].to(dev, non_blocking=True)
+        pipe.run(d)
+        pipe.fetch(pinned)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_fits = 0
+    d2h = 0
+    for k in range(args.steps):
+        d = stacks_host[(k + 2) % N_VARIANTS].to(dev, non_blocking=True)
+        pipe.run(d)
+        n, _, _, _, _ = pipe.fetch(pinned)
+        e2e_fits += n
+        d2h += pipe.d2h_bytes(n)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks, sum of work
+    if world > 1:
+        tt = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(tt[0].item()), float(tt[1].item())
+        cc = torch.tensor([fits_total, e2e_fits], dtype=torch.int64, device=dev)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        fits_all, e2e_fits_all = int(cc[0].item()), int(cc[1].item())
+    else:
+        e2e_ms = e2e_s * 1e3
+        fits_all, e2e_fits_all = fits_total, e2e_fits
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = fits_all / (ms_total * 1e-3)
+    frames_per_s = world * args.steps * N_FRAMES / (ms_total * 1e-3)
+    # ---- roofline of the dominant kernel (the LM fitter; FP64-pipe bound, never tensor cores)
+    peak = {}
+    for nm, flag in (("fp64", 1), ("fp32", 0)):
+        import ctypes
+        v = ctypes.c_double(0.0)
+        _lib.check(L.fsq_fma_peak(flag, ctypes.byref(v), None))
+        peak[nm] = v.value
+    flops = sum_niter * FLOP_PER_LM_ITER_5x5
+    achieved = flops / (fit_ms_avg * 1e-3) / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_file):
+        try:
+            hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"])
+            hbm_src = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    det_bytes = N_FRAMES * H * W * 2 + 8 * n_last
+    det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak["fp64"] / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / (peak["fp64"] / 1e12), "traffic": None,
+                "kernel": "lmfit_kernel<8,true> (fsq_fit_candidates)", "ms_per_launch": fit_ms_avg,
+                "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "nfev_per_launch": sum_nfev,
+                "flop_per_lm_iteration": FLOP_PER_LM_ITER_5x5,
+                "peak_source": "fsq_fma_peak FP64 FMA micro-benchmark, measured in this run (of measured)",
+                "fp32_fma_peak_tflops": peak["fp32"] / 1e12, "share_of_step": fit_ms_avg / (ms_total / args.steps)}
+    roofline_detect = {"bound": "hbm", "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": det_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                       "kernels": "detect_cm + thr + rowmask + scans + emit", "ms_per_launch": det_ms_avg,
+                       "algorithmic_bytes_per_launch": det_bytes,
+                       "note": "ALU-bound (99-comparator 5x5 median per pixel), see DESIGN.md"}
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = max(cores * 160, 256)
+        sample_frames = stacks_host[0].view(torch.int16).numpy().view(np.uint16)[:1]
+        r = cpu_reference_sample(sample_frames, n_sample, cores)
+        cpu = {"value": r["fits_per_s"], "unit": "fits/s", "cores": cores, "kind": _ref_kind(),
+               "sample": "%d random candidates of one 512x512 frame of the workload fitted on %d processes "
+                         "(%.1f s); detection on 1 full frame (%.3f s)" % (r["n_fits"], cores, r["t_fit"], r["t_detect_per_frame"]),
+               "frames_per_s": r["frames_per_s"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots (sigma 1.5), every frame: "
+                               "detection + 5x5 LM fit of every candidate + metrics",
+                   "frames_per_step": N_FRAMES, "candidates_per_step": n_probe,
+                   "solver": "minpack-clean" if args.clean else "minpack-faithful (reference behaviour incl. qrsolv diagonal view)",
+                   "l2": "8 different stacks cycled (168 MB > 126 MB L2): inputs larger than L2", "parallelism": "field-sharded x%d, no collective" % world},
+        "frames_per_s": frames_per_s,
+        "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": d2h // max(args.steps, 1), "frames_per_s": world * args.steps * N_FRAMES / (e2e_ms * 1e-3),
+                "api": "engine.FieldPipeline.run + fetch over fsq_detect / fsq_fit_candidates (pinned host frames in, packed results out)"},
+        "gpu_launches": args.steps * pipe.kernels_per_run,
+        "clocks": clocks, "roofline": roofline, "roofline_detect": roofline_detect,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clean", action="store_true", help="clean-MINPACK solver instead of the reference-faithful one")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

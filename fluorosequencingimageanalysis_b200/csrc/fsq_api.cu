@@ -1,0 +1,175 @@
+// libfsq: error channel, version, and the small per-spot kernels (fit-quality metrics on
+// arbitrary (sub_img, fit_img) pairs; photometry on spots).
+#include "fsq_common.cuh"
+#include <string.h>
+
+namespace fsq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    }
+    return n;
+}
+
+// ---- pflib.py:463-473 + illumina_s_n pflib.py:261-281; one thread per pair, sums in the
+// reference's (raster / edge-list) order --------------------------------------------------
+__global__ void __launch_bounds__(128)
+metrics_kernel(const long long* __restrict__ sub, const double* __restrict__ fit, long long n,
+               double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long* s = sub + i * 25;
+    const double* f = fit + i * 25;
+    long long isum = 0, imax = s[0];
+    for (int q = 0; q < 25; ++q) { isum += s[q]; imax = s[q] > imax ? s[q] : imax; }
+    const double mean = (double)isum / 25.0;
+    double ssr = 0.0, sst = 0.0;
+    for (int q = 0; q < 25; ++q) {
+        const double d = (double)s[q] - f[q];
+        ssr += d * d;
+        const double m = (double)s[q] - mean;
+        sst += m * m;
+    }
+    // edge list order of pflib.py:278-280: rows 0 and 4, then columns 0 and 4 of rows 1..3
+    long long esum = 0;
+    for (int c = 0; c < 5; ++c) esum += s[c] + s[20 + c];
+    for (int r = 1; r < 4; ++r) esum += s[r * 5] + s[r * 5 + 4];
+    const double emean = (double)esum / 16.0;
+    double ev = 0.0;
+    for (int c = 0; c < 5; ++c) { double e = (double)s[c] - emean; ev += e * e; }
+    for (int c = 0; c < 5; ++c) { double e = (double)s[20 + c] - emean; ev += e * e; }
+    for (int r = 1; r < 4; ++r) {
+        double e = (double)s[r * 5] - emean; ev += e * e;
+        e = (double)s[r * 5 + 4] - emean; ev += e * e;
+    }
+    out[i * 3 + 0] = 1.0 - ssr / sst;
+    out[i * 3 + 1] = sqrt(ssr / 25.0);
+    out[i * 3 + 2] = ((double)imax - emean) / sqrt(ev / 16.0);
+}
+
+__device__ __forceinline__ int load_pix_i(const void* base, int dtype, size_t off) {
+    switch (dtype) {
+        case FSQ_U8:  return (int)((const uint8_t*)base)[off];
+        case FSQ_U16: return (int)((const uint16_t*)base)[off];
+        case FSQ_I16: return (int)((const int16_t*)base)[off];
+        default:      return ((const int32_t*)base)[off];
+    }
+}
+
+// ---- flexlibrary.Spot photometry; one warp per spot -------------------------------------------
+//  method 0 simple   : sum of the (border-truncated) slice of radius `radius`    flexlibrary.py:160-170
+//  method 1 mexican  : sum(crown) - len(crown)*median(brim), slice-LOCAL indices flexlibrary.py:172-210
+//  method 2 maximum  : max of the slice                                          flexlibrary.py:264-284
+constexpr int PH_MAXR = 12;
+constexpr int PH_MAXN = (2 * PH_MAXR + 1) * (2 * PH_MAXR + 1);
+
+__global__ void __launch_bounds__(128)
+photometry_kernel(const void* __restrict__ frames, int dtype, int H, int W,
+                  const int32_t* __restrict__ hw, const int32_t* __restrict__ fr, long long n,
+                  int method, int radius, int brim, double* __restrict__ out) {
+    __shared__ int vals[4][PH_MAXN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const int h = hw[2 * i], w = hw[2 * i + 1];
+    const size_t fbase = (size_t)fr[i] * H * W;
+    const int r0 = max(0, h - radius), r1 = min(H, h + radius + 1);
+    const int c0 = max(0, w - radius), c1 = min(W, w + radius + 1);
+    const int sh = max(r1 - r0, 0), sw = max(c1 - c0, 0);
+    const int ns = sh * sw;
+    const int diameter = 2 * radius + 1;
+    long long tot = 0, crown_sum = 0;
+    int crown_n = 0, mx = -2147483647 - 1, nb = 0;
+    // pass 1: sums; brim values compacted into shared memory in slice raster order
+    for (int base = 0; base < ns; base += 32) {
+        const int q = base + lane;
+        bool is_brim = false;
+        int v = 0;
+        if (q < ns) {
+            const int lh = q / sw, lw = q - lh * sw;
+            v = load_pix_i(frames, dtype, fbase + (size_t)(r0 + lh) * W + (c0 + lw));
+            tot += v;
+            mx = max(mx, v);
+            const bool crown = (brim <= lh && lh < diameter - brim && brim <= lw && lw < diameter - brim);
+            if (crown) { crown_sum += v; ++crown_n; } else is_brim = true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_brim);
+        if (is_brim) vals[warp][nb + __popc(m & ((1u << lane) - 1u))] = v;
+        nb += __popc(m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, m);
+        crown_sum += __shfl_xor_sync(0xffffffffu, crown_sum, m);
+        crown_n += __shfl_xor_sync(0xffffffffu, crown_n, m);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    }
+    __syncwarp();
+    double res;
+    if (method == 0) res = (double)tot;
+    else if (method == 2) res = (double)mx;
+    else {
+        // median of the nb brim values by rank counting; even count -> mean of the two middle
+        const int k_lo = (nb - 1) / 2, k_hi = nb / 2;
+        long long pick = 0;     // sum of the (one or two) middle elements
+        for (int a = lane; a < nb; a += 32) {
+            const int va = vals[warp][a];
+            int c = 0;
+            for (int b = 0; b < nb; ++b) { const int vb = vals[warp][b]; c += (vb < va) || (vb == va && b < a); }
+            if (c == k_lo) pick += va;
+            if (c == k_hi) pick += va;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) pick += __shfl_xor_sync(0xffffffffu, pick, m);
+        const double med = nb > 0 ? (double)pick / 2.0 : __longlong_as_double(0x7ff8000000000000LL);
+        res = (double)crown_sum - (double)crown_n * med;
+    }
+    if (lane == 0) out[i] = res;
+}
+
+}  // namespace fsq
+
+using namespace fsq;
+
+extern "C" int fsq_version(void) { return FSQ_VERSION; }
+extern "C" const char* fsq_last_error(void) { return g_err; }
+
+extern "C" int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream) {
+    if (n < 0) { set_error("fsq_metrics: n < 0"); return FSQ_E_ARG; }
+    if (n == 0) return FSQ_OK;
+    if (!sub || !fit || !out) { set_error("fsq_metrics: NULL pointer argument"); return FSQ_E_ARG; }
+    metrics_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const long long*)sub, fit, n, out);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
+
+extern "C" int fsq_photometry(const void* frames, int dtype_code, int n_frames, int H, int W,
+                              const int32_t* spots_hw, const int32_t* spot_frame, int64_t n,
+                              int method, int radius, int brim, double* out, void* stream) {
+    if (n < 0) { set_error("fsq_photometry: n < 0"); return FSQ_E_ARG; }
+    if (n == 0) return FSQ_OK;
+    if (!frames || !spots_hw || !spot_frame || !out) { set_error("fsq_photometry: NULL pointer argument"); return FSQ_E_ARG; }
+    if (method < 0 || method > 2) { set_error("fsq_photometry: Uknown method specified."); return FSQ_E_ARG; }
+    if (radius < 0 || radius > PH_MAXR) { set_error("fsq_photometry: radius must be in 0..%d", PH_MAXR); return FSQ_E_ARG; }
+    if (dtype_code != FSQ_U8 && dtype_code != FSQ_U16 && dtype_code != FSQ_I16 && dtype_code != FSQ_I32) {
+        set_error("fsq_photometry: unsupported frame dtype code %d", dtype_code);
+        return FSQ_E_ARG;
+    }
+    (void)n_frames;
+    photometry_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(frames, dtype_code, H, W, spots_hw,
+                                                                                 spot_frame, n, method, radius, brim, out);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}

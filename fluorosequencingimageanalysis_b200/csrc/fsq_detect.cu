@@ -1,0 +1,443 @@
+// Candidate detection for a batch of frames (replaces pflib._psf_candidates, pflib.py:217-258).
+//
+//   pass A  detect_cm_kernel    tile-staged: raw tile (+halo, scipy 'reflect' borders) -> shared
+//                               memory -> s x s median (99-comparator selection network for
+//                               s = 5) -> mf = v - min(med, v) -> k x k integer correlation in
+//                               int64 -> clamp -> cm (saturated u32 scratch) + exact per-frame
+//                               integer moments  sum(cm), sum(cm^2) (three 64-bit limbs)
+//   pass T  detect_thr_kernel   thr = mean + c_std * std from the exact moments (128-bit integer
+//                               variance numerator, one sqrt)                      pflib.py:250
+//   pass B  detect_rowmask / scans / detect_emit   per-row ballot masks -> exclusive scans ->
+//                               raster-ordered (h, w) list, 2-px border excluded   pflib.py:252-257
+//
+// Algorithmic bytes per frame: H*W*sizeof(pixel) read + 8*N_cand written.
+#include "fsq_common.cuh"
+
+namespace fsq {
+
+constexpr int TW = 64;     // output tile width
+constexpr int TH = 32;     // output tile height
+constexpr int NT = 256;    // threads per block (pass A)
+constexpr int MAXS = 9;    // largest median window side
+constexpr int MAXK = 9;    // largest correlation template side
+constexpr int RAW_MAX = (TH + (MAXK - 1) + (MAXS - 1)) * (TW + (MAXK - 1) + (MAXS - 1));
+constexpr int MF_MAX = (TH + (MAXK - 1)) * (TW + (MAXK - 1));
+constexpr int CM_SPLIT = 20;               // cm = a * 2^20 + b
+constexpr int NSUM = 8;                    // u64 slots per frame in the moment scratch
+
+struct KParam { int k[MAXK * MAXK]; };
+
+struct DetectScratch {
+    uint32_t* cm32;                 // [F*H*W]
+    unsigned long long* sums;       // [F*NSUM]  s1, saa, sab, sbb, range-flag
+    int32_t* rowcount;              // [F*H]
+    int32_t* rowoff;                // [F*H]
+    int64_t* framebase;             // [F+1]
+    uint32_t* masks;                // [F*H*ceil(W/32)]
+    int32_t* flags;                 // [4]
+};
+
+static inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
+
+static int64_t carve(DetectScratch* s, char* base, int F, int H, int W) {
+    int64_t off = 0;
+    const int64_t npx = int64_t(F) * H * W;
+    const int64_t nrow = int64_t(F) * H;
+    const int64_t nw = (W + 31) / 32;
+    auto take = [&](int64_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
+    char* p;
+    p = take(npx * 4);               if (s) s->cm32 = (uint32_t*)p;
+    p = take(int64_t(F) * NSUM * 8); if (s) s->sums = (unsigned long long*)p;
+    p = take(nrow * 4);              if (s) s->rowcount = (int32_t*)p;
+    p = take(nrow * 4);              if (s) s->rowoff = (int32_t*)p;
+    p = take((int64_t(F) + 1) * 8);  if (s) s->framebase = (int64_t*)p;
+    p = take(nrow * nw * 4);         if (s) s->masks = (uint32_t*)p;
+    p = take(64);                    if (s) s->flags = (int32_t*)p;
+    return off;
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy.ndimage mode='reflect' == numpy 'symmetric':  d c b a | a b c d | d c b a
+    if (n == 1) return 0;
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - 1 - i;
+}
+
+#define FSQ_CE(a, b) { const int _lo = min(p[a], p[b]); const int _hi = max(p[a], p[b]); p[a] = _lo; p[b] = _hi; }
+
+// Median of 25 by a 99-comparator selection network (verified exhaustively over all 2^25
+// 0/1 inputs in tests/test_median_network.py; 0-1 principle).
+__device__ __forceinline__ int median25(int* p) {
+    FSQ_CE(0, 1) FSQ_CE(3, 4) FSQ_CE(2, 4) FSQ_CE(2, 3) FSQ_CE(6, 7) FSQ_CE(5, 7) FSQ_CE(5, 6)
+    FSQ_CE(9, 10) FSQ_CE(8, 10) FSQ_CE(8, 9) FSQ_CE(12, 13) FSQ_CE(11, 13) FSQ_CE(11, 12)
+    FSQ_CE(15, 16) FSQ_CE(14, 16) FSQ_CE(14, 15) FSQ_CE(18, 19) FSQ_CE(17, 19) FSQ_CE(17, 18)
+    FSQ_CE(21, 22) FSQ_CE(20, 22) FSQ_CE(20, 21) FSQ_CE(23, 24) FSQ_CE(2, 5) FSQ_CE(3, 6)
+    FSQ_CE(0, 6) FSQ_CE(0, 3) FSQ_CE(4, 7) FSQ_CE(1, 7) FSQ_CE(1, 4) FSQ_CE(11, 14) FSQ_CE(8, 14)
+    FSQ_CE(8, 11) FSQ_CE(12, 15) FSQ_CE(9, 15) FSQ_CE(9, 12) FSQ_CE(13, 16) FSQ_CE(10, 16)
+    FSQ_CE(10, 13) FSQ_CE(20, 23) FSQ_CE(17, 23) FSQ_CE(17, 20) FSQ_CE(21, 24) FSQ_CE(18, 24)
+    FSQ_CE(18, 21) FSQ_CE(19, 22) FSQ_CE(8, 17) FSQ_CE(9, 18) FSQ_CE(0, 18) FSQ_CE(0, 9)
+    FSQ_CE(10, 19) FSQ_CE(1, 19) FSQ_CE(1, 10) FSQ_CE(11, 20) FSQ_CE(2, 20) FSQ_CE(2, 11)
+    FSQ_CE(12, 21) FSQ_CE(3, 21) FSQ_CE(3, 12) FSQ_CE(13, 22) FSQ_CE(4, 22) FSQ_CE(4, 13)
+    FSQ_CE(14, 23) FSQ_CE(5, 23) FSQ_CE(5, 14) FSQ_CE(15, 24) FSQ_CE(6, 24) FSQ_CE(6, 15)
+    FSQ_CE(7, 16) FSQ_CE(7, 19) FSQ_CE(13, 21) FSQ_CE(15, 23) FSQ_CE(7, 13) FSQ_CE(7, 15)
+    FSQ_CE(1, 9) FSQ_CE(3, 11) FSQ_CE(5, 17) FSQ_CE(11, 17) FSQ_CE(9, 17) FSQ_CE(4, 10)
+    FSQ_CE(6, 12) FSQ_CE(7, 14) FSQ_CE(4, 6) FSQ_CE(4, 7) FSQ_CE(12, 14) FSQ_CE(10, 14)
+    FSQ_CE(6, 7) FSQ_CE(10, 12) FSQ_CE(6, 10) FSQ_CE(6, 17) FSQ_CE(12, 17) FSQ_CE(7, 17)
+    FSQ_CE(7, 10) FSQ_CE(12, 18) FSQ_CE(7, 12) FSQ_CE(10, 18) FSQ_CE(12, 20) FSQ_CE(10, 20)
+    FSQ_CE(10, 12)
+    return p[12];
+}
+#undef FSQ_CE
+
+// Generic rank-(n/2) selection by counting (used only for non-default median sizes).
+__device__ int median_generic(const int* raw, int RW, int y0, int x0, int s) {
+    const int n = s * s;
+    const int want = n / 2;
+    for (int a = 0; a < n; ++a) {
+        const int va = raw[(y0 + a / s) * RW + x0 + a % s];
+        int c = 0;
+        for (int b = 0; b < n; ++b) {
+            const int vb = raw[(y0 + b / s) * RW + x0 + b % s];
+            c += (vb < va) || (vb == va && b < a);
+        }
+        if (c == want) return va;
+    }
+    return 0;
+}
+
+template <typename PixT, int S, int K>
+__global__ void __launch_bounds__(NT)
+detect_cm_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp, int s_rt, int k_rt,
+                 uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums) {
+    const int s = S ? S : s_rt;
+    const int k = K ? K : k_rt;
+    const int mlo = s / 2, mhi = s - 1 - mlo, kh = k / 2;
+    const int RW = TW + 2 * kh + mlo + mhi, RH = TH + 2 * kh + mlo + mhi;
+    const int MW = TW + 2 * kh, MH = TH + 2 * kh;
+    __shared__ int raw[RAW_MAX];
+    __shared__ int mf[MF_MAX];
+    __shared__ unsigned long long red[4][NT / 32];
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const PixT* img = frames + size_t(frame) * H * W;
+
+    // stage the raw tile (reflected at the image border)
+    for (int idx = tid; idx < RH * RW; idx += NT) {
+        const int ry = idx / RW, rx = idx - ry * RW;
+        const int gy = reflect_idx(ty0 - kh - mlo + ry, H);
+        const int gx = reflect_idx(tx0 - kh - mlo + rx, W);
+        raw[idx] = (int)img[size_t(gy) * W + gx];
+    }
+    __syncthreads();
+
+    // background removal: mf = v - min(median, v); zero outside the image (correlate pads with 0)
+    for (int idx = tid; idx < MH * MW; idx += NT) {
+        const int my = idx / MW, mx = idx - my * MW;
+        const int gy = ty0 - kh + my, gx = tx0 - kh + mx;
+        int out = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const int v = raw[(my + mlo) * RW + mx + mlo];
+            int med;
+            if (S == 5) {
+                int p[25];
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) p[i * 5 + j] = raw[(my + i) * RW + mx + j];
+                med = median25(p);
+            } else {
+                med = median_generic(raw, RW, my, mx, s);
+            }
+            out = v - min(med, v);
+        }
+        mf[idx] = out;
+    }
+    __syncthreads();
+
+    // correlation, clamp, store, exact moments
+    unsigned long long s1 = 0, saa = 0, sab = 0, sbb = 0, bad = 0;
+    for (int idx = tid; idx < TH * TW; idx += NT) {
+        const int oy = idx / TW, ox = idx - oy * TW;
+        const int gy = ty0 + oy, gx = tx0 + ox;
+        if (gy < H && gx < W) {
+            long long acc = 0;
+            if (K == 5) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        acc += (long long)kp.k[i * 5 + j] * (long long)mf[(oy + i) * MW + ox + j];
+            } else {
+                for (int i = 0; i < k; ++i)
+                    for (int j = 0; j < k; ++j)
+                        acc += (long long)kp.k[i * k + j] * (long long)mf[(oy + i) * MW + ox + j];
+            }
+            const unsigned long long cm = acc > 0 ? (unsigned long long)acc : 0ull;
+            cm32[(size_t(frame) * H + gy) * W + gx] = cm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cm;
+            const unsigned long long a = cm >> CM_SPLIT, b = cm & ((1ull << CM_SPLIT) - 1);
+            bad |= (a >> 21);                  // cm >= 2^41 would overflow the limb sums
+            s1 += cm; saa += a * a; sab += a * b; sbb += b * b;
+        }
+    }
+    // block reduction -> one atomic per block and limb
+    unsigned long long v[4] = {s1, saa, sab, sbb};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], m);
+        if ((tid & 31) == 0) red[q][tid >> 5] = v[q];
+    }
+    bad = __any_sync(0xffffffffu, bad != 0);
+    if (bad && (tid & 31) == 0) atomicOr(&sums[size_t(frame) * NSUM + 4], 1ull);
+    __syncthreads();
+    if (tid < 4) {
+        unsigned long long t = 0;
+        for (int w = 0; w < NT / 32; ++w) t += red[tid][w];
+        atomicAdd(&sums[size_t(frame) * NSUM + tid], t);
+    }
+}
+
+__global__ void detect_thr_kernel(const unsigned long long* __restrict__ sums, int F, long long N,
+                                  double c_std, double* __restrict__ thr, int32_t* flags) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const unsigned long long s1 = sums[size_t(f) * NSUM + 0];
+    const unsigned long long saa = sums[size_t(f) * NSUM + 1];
+    const unsigned long long sab = sums[size_t(f) * NSUM + 2];
+    const unsigned long long sbb = sums[size_t(f) * NSUM + 3];
+    if (sums[size_t(f) * NSUM + 4]) atomicOr(&flags[0], 1);
+    typedef unsigned __int128 u128;
+    const u128 s2 = ((u128)saa << (2 * CM_SPLIT)) + ((u128)sab << (CM_SPLIT + 1)) + (u128)sbb;
+    const u128 d = (u128)(unsigned long long)N * s2 - (u128)s1 * (u128)s1;   // N*sum(x^2) - sum(x)^2 >= 0
+    const double dd = (double)(unsigned long long)(d >> 64) * 18446744073709551616.0 +
+                      (double)(unsigned long long)d;
+    const double mean = (double)s1 / (double)N;
+    const double sd = sqrt(dd) / (double)N;
+    const double t = mean + c_std * sd;
+    thr[f] = t;
+    if (t > 4294967294.0) atomicOr(&flags[0], 2);   // beyond the saturated u32 scratch
+}
+
+// one warp per image row: threshold test -> ballot masks + row count
+__global__ void __launch_bounds__(256)
+detect_rowmask_kernel(const uint32_t* __restrict__ cm32, const double* __restrict__ thr,
+                      long long nrows, int H, int W, uint32_t* __restrict__ masks,
+                      int32_t* __restrict__ rowcount) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    const int f = int(row / H), y = int(row - (long long)f * H);
+    const double t = thr[f];
+    const int nw = (W + 31) / 32;
+    const bool yok = (y >= 2) && (y < H - 2);
+    const uint32_t* src = cm32 + size_t(row) * W;
+    int count = 0;
+    for (int wi = 0; wi < nw; ++wi) {
+        const int x = wi * 32 + lane;
+        bool pred = false;
+        if (yok && x >= 2 && x < W - 2) pred = !((double)src[x] < t);     // kept when NOT '<'
+        const unsigned m = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0) masks[size_t(row) * nw + wi] = m;
+        count += __popc(m);
+    }
+    if (lane == 0) rowcount[row] = count;
+}
+
+// exclusive scan of one frame's row counts (block per frame)
+__global__ void __launch_bounds__(256)
+detect_rowscan_kernel(const int32_t* __restrict__ rowcount, int H, int32_t* __restrict__ rowoff,
+                      int64_t* __restrict__ n_cand) {
+    __shared__ int buf[256];
+    __shared__ int carry;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < H; base += 256) {
+        const int y = base + tid;
+        const int v = y < H ? rowcount[size_t(f) * H + y] : 0;
+        buf[tid] = v;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const int t = tid >= d ? buf[tid - d] : 0;
+            __syncthreads();
+            buf[tid] += t;
+            __syncthreads();
+        }
+        if (y < H) rowoff[size_t(f) * H + y] = carry + buf[tid] - v;
+        __syncthreads();
+        if (tid == 255) carry += buf[255];
+        __syncthreads();
+    }
+    if (tid == 0) n_cand[f] = carry;
+}
+
+// exclusive scan of the per-frame totals (single block)
+__global__ void __launch_bounds__(1024)
+detect_framescan_kernel(int64_t* __restrict__ n_cand, int F, int64_t* __restrict__ framebase) {
+    __shared__ long long buf[1024];
+    __shared__ long long carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < F; base += 1024) {
+        const int f = base + tid;
+        const long long v = f < F ? n_cand[f] : 0;
+        buf[tid] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            const long long t = tid >= d ? buf[tid - d] : 0;
+            __syncthreads();
+            buf[tid] += t;
+            __syncthreads();
+        }
+        if (f < F) framebase[f] = carry + buf[tid] - v;
+        __syncthreads();
+        if (tid == 1023) carry += buf[1023];
+        __syncthreads();
+    }
+    if (tid == 0) { framebase[F] = carry; n_cand[F] = carry; }
+}
+
+__global__ void __launch_bounds__(256)
+detect_emit_kernel(const uint32_t* __restrict__ masks, const int32_t* __restrict__ rowoff,
+                   const int64_t* __restrict__ framebase, long long nrows, int H, int W,
+                   int32_t* __restrict__ cand_hw, int32_t* __restrict__ cand_frame, long long cap) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    const int f = int(row / H), y = int(row - (long long)f * H);
+    const int nw = (W + 31) / 32;
+    long long pos = framebase[f] + rowoff[row];
+    for (int wi = 0; wi < nw; ++wi) {
+        const unsigned m = masks[size_t(row) * nw + wi];
+        if (m == 0) continue;
+        if ((m >> lane) & 1u) {
+            const long long idx = pos + __popc(m & ((1u << lane) - 1u));
+            if (idx < cap) {
+                cand_hw[2 * idx] = y;
+                cand_hw[2 * idx + 1] = wi * 32 + lane;
+                cand_frame[idx] = f;
+            }
+        }
+        pos += __popc(m);
+    }
+}
+
+template <typename PixT>
+static int launch_cm(const void* frames, int F, int H, int W, const KParam& kp, int s, int k,
+                     const DetectScratch& sc, cudaStream_t st) {
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, F);
+    if (s == 5 && k == 5)
+        detect_cm_kernel<PixT, 5, 5><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, s, k, sc.cm32, sc.sums);
+    else
+        detect_cm_kernel<PixT, 0, 0><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, s, k, sc.cm32, sc.sums);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
+
+}  // namespace fsq
+
+using namespace fsq;
+
+extern "C" int64_t fsq_detect_scratch_bytes(int n_frames, int H, int W) {
+    if (n_frames <= 0 || H <= 0 || W <= 0) return 0;
+    return carve(nullptr, nullptr, n_frames, H, W);
+}
+
+extern "C" int fsq_detect(const void* frames, int dtype_code, int n_frames, int H, int W,
+                          const int64_t* K_host, int ksize, int mf_size, double c_std,
+                          int32_t* cand_hw, int32_t* cand_frame, int64_t* n_cand, double* thr,
+                          int64_t cap, void* scratch, int64_t scratch_bytes, void* stream) {
+    if (!frames || !K_host || !cand_hw || !cand_frame || !n_cand || !thr || !scratch) {
+        set_error("fsq_detect: NULL pointer argument");
+        return FSQ_E_ARG;
+    }
+    if (n_frames <= 0 || H <= 0 || W <= 0 || cap < 0) {
+        set_error("fsq_detect: bad shape n_frames=%d H=%d W=%d cap=%lld", n_frames, H, W, (long long)cap);
+        return FSQ_E_ARG;
+    }
+    if (ksize < 1 || ksize > MAXK || (ksize % 2) == 0) {
+        set_error("fsq_detect: correlation_matrix must be square with an odd side <= %d (got %d)", MAXK, ksize);
+        return FSQ_E_ARG;
+    }
+    if (mf_size < 1 || mf_size > MAXS) {
+        set_error("fsq_detect: median_filter_size must be in 1..%d (got %d)", MAXS, mf_size);
+        return FSQ_E_ARG;
+    }
+    if (n_frames > 65535) {
+        set_error("fsq_detect: at most 65535 frames per call (got %d); split the batch", n_frames);
+        return FSQ_E_ARG;
+    }
+    KParam kp;
+    for (int i = 0; i < MAXK * MAXK; ++i) kp.k[i] = 0;
+    for (int i = 0; i < ksize * ksize; ++i) {
+        if (K_host[i] > 2147483647LL || K_host[i] < -2147483647LL) {
+            set_error("fsq_detect: correlation_matrix entries must fit in int32");
+            return FSQ_E_RANGE;
+        }
+        kp.k[i] = (int)K_host[i];
+    }
+    const int64_t need = carve(nullptr, nullptr, n_frames, H, W);
+    if (scratch_bytes < need) {
+        set_error("fsq_detect: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)need);
+        return FSQ_E_CAPACITY;
+    }
+    DetectScratch sc;
+    carve(&sc, (char*)scratch, n_frames, H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    FSQ_CUDA_CHECK(cudaMemsetAsync(sc.sums, 0, size_t(n_frames) * NSUM * 8, st));
+    FSQ_CUDA_CHECK(cudaMemsetAsync(sc.flags, 0, 64, st));
+    int rc;
+    switch (dtype_code) {
+        case FSQ_U8:  rc = launch_cm<uint8_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
+        case FSQ_U16: rc = launch_cm<uint16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
+        case FSQ_I16: rc = launch_cm<int16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
+        case FSQ_I32: rc = launch_cm<int32_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
+        default:
+            set_error("fsq_detect: unsupported dtype code %d", dtype_code);
+            return FSQ_E_ARG;
+    }
+    if (rc != FSQ_OK) return rc;
+    detect_thr_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(sc.sums, n_frames, (long long)H * W, c_std, thr, sc.flags);
+    FSQ_LAUNCH_CHECK();
+    const long long nrows = (long long)n_frames * H;
+    const unsigned rb = (unsigned)((nrows + 7) / 8);
+    detect_rowmask_kernel<<<rb, 256, 0, st>>>(sc.cm32, thr, nrows, H, W, sc.masks, sc.rowcount);
+    FSQ_LAUNCH_CHECK();
+    detect_rowscan_kernel<<<n_frames, 256, 0, st>>>(sc.rowcount, H, sc.rowoff, n_cand);
+    FSQ_LAUNCH_CHECK();
+    detect_framescan_kernel<<<1, 1024, 0, st>>>(n_cand, n_frames, sc.framebase);
+    FSQ_LAUNCH_CHECK();
+    detect_emit_kernel<<<rb, 256, 0, st>>>(sc.masks, sc.rowoff, sc.framebase, nrows, H, W, cand_hw, cand_frame, (long long)cap);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
+
+// flags[0] bit0: cm >= 2^41 somewhere; bit1: threshold beyond the u32 scratch.  Host-visible
+// through fsq_detect_flags (synchronises the stream).
+extern "C" int fsq_detect_flags(const void* scratch, int n_frames, int H, int W, void* stream) {
+    DetectScratch sc;
+    carve(&sc, (char*)scratch, n_frames, H, W);
+    int32_t h = 0;
+    FSQ_CUDA_CHECK(cudaMemcpyAsync(&h, sc.flags, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FSQ_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h) {
+        set_error("fsq_detect: data outside the exact range (flags=%d: 1=correlation >= 2^41, 2=threshold > 2^32)", h);
+        return FSQ_E_RANGE;
+    }
+    return FSQ_OK;
+}
+
+extern "C" int fsq_detect_copy_cm32(const void* scratch, int n_frames, int H, int W, uint32_t* cm32_out,
+                                    void* stream) {
+    if (!scratch || !cm32_out) { set_error("fsq_detect_copy_cm32: NULL"); return FSQ_E_ARG; }
+    DetectScratch sc;
+    carve(&sc, (char*)scratch, n_frames, H, W);
+    FSQ_CUDA_CHECK(cudaMemcpyAsync(cm32_out, sc.cm32, size_t(n_frames) * H * W * 4,
+                                   cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FSQ_OK;
+}

@@ -1,0 +1,414 @@
+"""
+Batched device API above the C-ABI: frames in, packed per-candidate arrays out.
+
+These are the additions SURVEY.md section 8(b) describes (``find_peptides_batch``,
+``gaussfit_batch``); the reference-signature single-call functions in ``pflib.py`` /
+``gaussfitter.py`` are batch-of-one wrappers around them.  All tensors are torch CUDA tensors
+(torch = device memory + streams only); every compute step is a kernel of libfsq.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DEFAULT_CORRELATION_MATRIX = np.array(            # pflib.py:48-52
+    [[-5935, -5935, -5935, -5935, -5935],
+     [-5935, 8027, 8027, 8027, -5935],
+     [-5935, 8027, 30742, 8027, -5935],
+     [-5935, 8027, 8027, 8027, -5935],
+     [-5935, -5935, -5935, -5935, -5935]], dtype=np.int64)
+
+_TORCH_DTYPE_CODE = {torch.uint8: _lib.FSQ_U8, torch.int16: _lib.FSQ_I16, torch.int32: _lib.FSQ_I32,
+                     torch.float64: _lib.FSQ_F64, torch.int64: _lib.FSQ_I64}
+if hasattr(torch, "uint16"):
+    _TORCH_DTYPE_CODE[torch.uint16] = _lib.FSQ_U16
+
+# out_fit columns of fit_candidates (fsq.h): image-coordinate PSF record
+COL_H0, COL_W0, COL_H, COL_A, COL_SIGMA_H, COL_SIGMA_W, COL_THETA, COL_RMSE, COL_R2, COL_SN, COL_CHI2 = range(11)
+ICOL_STATUS, ICOL_NITER, ICOL_NFEV, ICOL_NQRSOLV = range(4)
+
+MAX_FRAMES_PER_CALL = 65535
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("fluorosequencingimageanalysis_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+    _lib.load()
+
+
+def to_device_frames(frames, device=None):
+    """Accepts numpy / torch, 2-D or 3-D, any integer dtype the reference would take
+    (pflib.py:241 casts to int64); returns a contiguous CUDA tensor [F,H,W] of a supported
+    pixel dtype."""
+    require_cuda()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    if isinstance(frames, np.ndarray):
+        a = frames
+        if a.dtype == np.uint16:
+            t = torch.from_numpy(a.view(np.int16)).view(torch.uint16)
+        elif a.dtype in (np.uint8, np.int16, np.int32):
+            t = torch.from_numpy(a)
+        elif a.dtype.kind in "iu":
+            if a.size and (a.min() < -2 ** 30 or a.max() >= 2 ** 30):
+                raise OverflowError("pixel values beyond +-2^30 are outside the exact range of the kernels")
+            t = torch.from_numpy(a.astype(np.int32))
+        elif a.dtype.kind == "b":
+            t = torch.from_numpy(a.astype(np.uint8))
+        else:
+            raise TypeError("frames must have an integer dtype (got %s)" % a.dtype)
+        t = t.to(device, non_blocking=True)
+    else:
+        t = frames
+        if t.dtype == torch.int64:
+            t = t.to(torch.int32)
+        if t.dtype not in _TORCH_DTYPE_CODE or t.dtype in (torch.float64,):
+            raise TypeError("unsupported frame dtype %s" % t.dtype)
+        t = t.to(device)
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError("frames must be [H,W] or [F,H,W]")
+    return t.contiguous()
+
+
+def _check_kernel(correlation_matrix):
+    K = np.asarray(correlation_matrix)
+    if K.ndim != 2 or K.shape[0] != K.shape[1] or K.shape[0] % 2 == 0:      # pflib.py:236-239
+        raise ValueError("correlation_matrix must be square, with an odd "
+                         "number of rows and columns")
+    if K.dtype.kind not in "iub":
+        if not np.all(K == np.rint(K)):
+            raise ValueError("correlation_matrix must hold integers (the reference correlates in int64)")
+    return np.ascontiguousarray(K.astype(np.int64))
+
+
+class Detection(object):
+    """Packed result of detect_batch: device tensors, raster order inside a frame."""
+    __slots__ = ("cand_hw", "cand_frame", "n_cand", "thr", "total", "scratch", "shape")
+
+    def per_frame(self):
+        """-> list (per frame) of int32 numpy [n,2] arrays (one D2H copy)."""
+        hw = self.cand_hw[:self.total].cpu().numpy()
+        counts = self.n_cand[:-1].cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        return [hw[offs[i]:offs[i + 1]] for i in range(len(counts))]
+
+
+def detect_batch(frames, median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX,
+                 c_std=2, cap=None, keep_scratch=False):
+    """pflib._psf_candidates (pflib.py:217-258) for a batch of frames on the GPU."""
+    L = _lib.load()
+    frames = to_device_frames(frames)
+    F, H, W = frames.shape
+    if F > MAX_FRAMES_PER_CALL:
+        raise ValueError("at most %d frames per call" % MAX_FRAMES_PER_CALL)
+    K = _check_kernel(correlation_matrix)
+    dev = frames.device
+    code = _TORCH_DTYPE_CODE[frames.dtype]
+    sbytes = L.fsq_detect_scratch_bytes(F, H, W)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    n_cand = torch.empty(F + 1, dtype=torch.int64, device=dev)
+    thr = torch.empty(F, dtype=torch.float64, device=dev)
+    if cap is None:
+        cap = max(4096, int(0.06 * F * H * W))
+    Kp = K.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+    while True:
+        cand_hw = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        cand_frame = torch.empty(cap, dtype=torch.int32, device=dev)
+        rc = L.fsq_detect(_ptr(frames), code, F, H, W, Kp, K.shape[0], int(median_filter_size),
+                          float(c_std), _ptr(cand_hw), _ptr(cand_frame), _ptr(n_cand), _ptr(thr),
+                          cap, _ptr(scratch), sbytes, _stream())
+        _lib.check(rc)
+        _lib.check(L.fsq_detect_flags(_ptr(scratch), F, H, W, _stream()))     # synchronises
+        total = int(n_cand[F].item())
+        if total <= cap:
+            break
+        cap = total                                                           # FSQ_E_CAPACITY protocol
+    d = Detection()
+    d.cand_hw, d.cand_frame, d.n_cand, d.thr, d.total = cand_hw, cand_frame, n_cand, thr, total
+    d.scratch = scratch if keep_scratch else None
+    d.shape = (F, H, W)
+    return d
+
+
+def detect_cm32(det):
+    """Clamped correlation map (saturated to uint32) of the last detect_batch(keep_scratch=True)."""
+    L = _lib.load()
+    F, H, W = det.shape
+    out = torch.empty((F, H, W), dtype=torch.int32, device=det.cand_hw.device)
+    _lib.check(L.fsq_detect_copy_cm32(_ptr(det.scratch), F, H, W, _ptr(out), _stream()))
+    return out.cpu().numpy().view(np.uint32)
+
+
+def fit_candidates(frames, cand_hw, cand_frame, n, faithful=True, want_fit_img=False, n_dev=None,
+                   opts=None):
+    """pflib.find_peptides' per-candidate loop (pflib.py:441-477) for n candidates.
+    Returns (out_fit [n,12] f64, out_int [n,4] i32, fit_img [n,25] f64 | None) on the device."""
+    L = _lib.load()
+    frames = to_device_frames(frames)
+    F, H, W = frames.shape
+    dev = frames.device
+    o = opts or _lib.default_opts(faithful=faithful)
+    out_fit = torch.empty((n, 12), dtype=torch.float64, device=dev)
+    out_int = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    fit_img = torch.empty((n, 25), dtype=torch.float64, device=dev) if want_fit_img else None
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out_fit, out_int, fit_img
+    rc = L.fsq_fit_candidates(_ptr(frames), _TORCH_DTYPE_CODE[frames.dtype], F, H, W, _ptr(cand_hw),
+                              _ptr(cand_frame), n, _ptr(n_dev), ctypes.byref(o), _ptr(out_fit),
+                              _ptr(out_int), _ptr(fit_img), _ptr(counter), _stream())
+    _lib.check(rc)
+    return out_fit, out_int, fit_img
+
+
+class FitBatch(object):
+    __slots__ = ("params", "perror", "status", "niter", "nfev", "chi2", "n_qrsolv", "fit_img")
+
+
+def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perror=False,
+                   want_fit_img=False, opts=None, **mpfit_kw):
+    """gaussfitter.gaussfit -> mpfit (agpy/gaussfitter.py:142-255) for n windows [n,win,win]."""
+    L = _lib.load()
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def dv(a, dt):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=dt).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+
+    if isinstance(windows, np.ndarray):
+        if windows.dtype.kind in "iub":
+            w = torch.from_numpy(np.ascontiguousarray(windows.astype(np.int64))).to(dev)
+        else:
+            w = torch.from_numpy(np.ascontiguousarray(windows.astype(np.float64))).to(dev)
+    else:
+        w = windows.to(dev).contiguous()
+        if w.dtype not in (torch.float64, torch.int64):
+            w = w.to(torch.float64 if w.dtype.is_floating_point else torch.int64)
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    n, win, win2 = w.shape
+    if win != win2:
+        raise ValueError("windows must be square")
+    p0 = dv(p0, torch.float64).reshape(n, 7)
+    lo = dv(lo, torch.float64).reshape(n, 7)
+    hi = dv(hi, torch.float64).reshape(n, 7)
+    lim_lo = dv(lim_lo, torch.uint8).reshape(n, 7)
+    lim_hi = dv(lim_hi, torch.uint8).reshape(n, 7)
+    o = opts or _lib.default_opts(faithful=faithful, want_perror=want_perror, **mpfit_kw)
+    r = FitBatch()
+    r.params = torch.empty((n, 7), dtype=torch.float64, device=dev)
+    r.perror = torch.empty((n, 7), dtype=torch.float64, device=dev) if want_perror else None
+    r.status = torch.empty(n, dtype=torch.int32, device=dev)
+    r.niter = torch.empty(n, dtype=torch.int32, device=dev)
+    r.nfev = torch.empty(n, dtype=torch.int32, device=dev)
+    r.chi2 = torch.empty(n, dtype=torch.float64, device=dev)
+    r.n_qrsolv = torch.empty(n, dtype=torch.int32, device=dev)
+    r.fit_img = torch.empty((n, win, win), dtype=torch.float64, device=dev) if want_fit_img else None
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    rc = L.fsq_gaussfit_batch(_ptr(w), _TORCH_DTYPE_CODE[w.dtype], n, win, _ptr(p0), _ptr(lo), _ptr(hi),
+                              _ptr(lim_lo), _ptr(lim_hi), ctypes.byref(o), _ptr(r.params), _ptr(r.perror),
+                              _ptr(r.status), _ptr(r.niter), _ptr(r.nfev), _ptr(r.chi2), _ptr(r.n_qrsolv),
+                              _ptr(r.fit_img), _ptr(counter), _stream())
+    _lib.check(rc)
+    return r
+
+
+def gaussfit_batch_trace(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, trace_steps=256):
+    """Debug/test variant of gaussfit_batch: returns (FitBatch, trace [n, trace_steps, 20] numpy)."""
+    L = _lib.load()
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    w = torch.from_numpy(np.ascontiguousarray(np.asarray(windows).astype(np.float64))).to(dev)
+    n, win, _ = w.shape
+    td = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev).reshape(n, 7)
+    p0, lo, hi = td(p0, torch.float64), td(lo, torch.float64), td(hi, torch.float64)
+    lim_lo, lim_hi = td(lim_lo, torch.uint8), td(lim_hi, torch.uint8)
+    o = _lib.default_opts(faithful=faithful)
+    r = FitBatch()
+    r.params = torch.empty((n, 7), dtype=torch.float64, device=dev)
+    r.status = torch.empty(n, dtype=torch.int32, device=dev)
+    r.niter = torch.empty(n, dtype=torch.int32, device=dev)
+    r.nfev = torch.empty(n, dtype=torch.int32, device=dev)
+    r.chi2 = torch.empty(n, dtype=torch.float64, device=dev)
+    r.n_qrsolv = torch.empty(n, dtype=torch.int32, device=dev)
+    r.perror = r.fit_img = None
+    trace = torch.zeros((n, trace_steps, 20), dtype=torch.float64, device=dev)
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    rc = L.fsq_gaussfit_batch_trace(_ptr(w), _lib.FSQ_F64, n, win, _ptr(p0), _ptr(lo), _ptr(hi), _ptr(lim_lo),
+                                    _ptr(lim_hi), ctypes.byref(o), _ptr(r.params), _ptr(r.status), _ptr(r.niter),
+                                    _ptr(r.nfev), _ptr(r.chi2), _ptr(r.n_qrsolv), _ptr(trace), trace_steps, n,
+                                    _ptr(counter), _stream())
+    _lib.check(rc)
+    return r, trace.cpu().numpy()
+
+
+def metrics_batch(sub, fit):
+    """pflib.py:463-473 for n (sub_img, fit_img) pairs -> [n,3] (r_2, rmse, s_n)."""
+    L = _lib.load()
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    s = torch.as_tensor(np.ascontiguousarray(np.asarray(sub, dtype=np.int64))).to(dev).reshape(-1, 25)
+    f = torch.as_tensor(np.ascontiguousarray(np.asarray(fit, dtype=np.float64))).to(dev).reshape(-1, 25)
+    out = torch.empty((s.shape[0], 3), dtype=torch.float64, device=dev)
+    _lib.check(L.fsq_metrics(_ptr(s), _ptr(f), s.shape[0], _ptr(out), _stream()))
+    return out
+
+
+PHOT_METHODS = {"simple": 0, "mexican_hat": 1, "maximum": 2}
+
+
+def photometry_batch(frames, spots_hw, spot_frame, method="mexican_hat", radius=None, brim_size=6,
+                     size=5):
+    """flexlibrary.Spot.photometry (flexlibrary.py:160-210, 264-284) for n spots -> [n] f64."""
+    L = _lib.load()
+    frames = to_device_frames(frames)
+    F, H, W = frames.shape
+    dev = frames.device
+    if method not in PHOT_METHODS:
+        raise ValueError("Uknown method specified.")                         # flexlibrary.py:315
+    if radius is None:
+        radius = {"simple": (size - 1) // 2, "mexican_hat": 9, "maximum": 5}[method]
+    hw = torch.as_tensor(np.ascontiguousarray(np.asarray(spots_hw, dtype=np.int32))).to(dev).reshape(-1, 2)
+    fr = torch.as_tensor(np.ascontiguousarray(np.asarray(spot_frame, dtype=np.int32))).to(dev).reshape(-1)
+    out = torch.empty(hw.shape[0], dtype=torch.float64, device=dev)
+    _lib.check(L.fsq_photometry(_ptr(frames), _TORCH_DTYPE_CODE[frames.dtype], F, H, W, _ptr(hw), _ptr(fr),
+                                hw.shape[0], PHOT_METHODS[method], int(radius), int(brim_size), _ptr(out),
+                                _stream()))
+    return out
+
+
+class FieldResults(object):
+    """Packed per-candidate results of find_peptides_batch (host numpy after .cpu())."""
+    __slots__ = ("cand_hw", "cand_frame", "n_cand", "thr", "fit", "ints", "fit_img", "shape")
+
+
+def find_peptides_batch(frames, median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX,
+                        c_std=2, faithful=True, want_fit_img=False, to_host=True):
+    """Detection + per-candidate fit + metrics for a batch of frames (the GPU-relevant part of
+    pflib.find_peptides, pflib.py:434-477).  The R^2 gate / consolidation / re-key
+    (pflib.py:466-468, 479-519) operate on these packed arrays -- see pflib.consolidate_packed."""
+    frames = to_device_frames(frames)
+    det = detect_batch(frames, median_filter_size, correlation_matrix, c_std)
+    fit, ints, fit_img = fit_candidates(frames, det.cand_hw, det.cand_frame, det.total,
+                                        faithful=faithful, want_fit_img=want_fit_img)
+    r = FieldResults()
+    r.shape = tuple(frames.shape)
+    if to_host:
+        r.cand_hw = det.cand_hw[:det.total].cpu().numpy()
+        r.cand_frame = det.cand_frame[:det.total].cpu().numpy()
+        r.n_cand = det.n_cand.cpu().numpy()
+        r.thr = det.thr.cpu().numpy()
+        r.fit = fit.cpu().numpy()
+        r.ints = ints.cpu().numpy()
+        r.fit_img = fit_img.cpu().numpy() if fit_img is not None else None
+    else:
+        r.cand_hw, r.cand_frame, r.n_cand, r.thr = det.cand_hw[:det.total], det.cand_frame[:det.total], det.n_cand, det.thr
+        r.fit, r.ints, r.fit_img = fit, ints, fit_img
+    return r
+
+
+class FieldPipeline(object):
+    """Pre-allocated, sync-free detection -> fit -> metrics pipeline for batches of a fixed
+    shape (the production path bench.py measures).  ``run`` only enqueues kernels on the
+    current stream: the candidate count stays on the device (fsq_fit_candidates reads it through
+    ``n_dev``); ``fetch`` does the one device->host copy of the packed results."""
+
+    def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
+                 median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
+                 device=None):
+        require_cuda()
+        self.L = _lib.load()
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.F, self.H, self.W = int(n_frames), int(H), int(W)
+        if self.F > MAX_FRAMES_PER_CALL:
+            raise ValueError("at most %d frames per pipeline batch" % MAX_FRAMES_PER_CALL)
+        self.dtype = dtype if dtype is not None else torch.uint16
+        self.code = _TORCH_DTYPE_CODE[self.dtype]
+        self.K = _check_kernel(correlation_matrix)
+        self.mf = int(median_filter_size)
+        self.c_std = float(c_std)
+        self.opts = _lib.default_opts(faithful=faithful)
+        if cap_per_frame is None:
+            cap_per_frame = max(1024, int(0.06 * H * W))
+        self.cap = int(cap_per_frame) * self.F
+        self.sbytes = self.L.fsq_detect_scratch_bytes(self.F, self.H, self.W)
+        d = self.dev
+        self.scratch = torch.empty(self.sbytes, dtype=torch.uint8, device=d)
+        self.cand_hw = torch.empty((self.cap, 2), dtype=torch.int32, device=d)
+        self.cand_frame = torch.empty(self.cap, dtype=torch.int32, device=d)
+        self.n_cand = torch.zeros(self.F + 1, dtype=torch.int64, device=d)
+        self.thr = torch.empty(self.F, dtype=torch.float64, device=d)
+        self.out_fit = torch.empty((self.cap, 12), dtype=torch.float64, device=d)
+        self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=d)
+        self.kernels_per_run = 7          # cm, thr, rowmask, rowscan, framescan, emit, lmfit
+
+    def run(self, frames_dev, fit=True):
+        """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype)."""
+        L = self.L
+        Kp = self.K.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        st = _stream()
+        _lib.check(L.fsq_detect(_ptr(frames_dev), self.code, self.F, self.H, self.W, Kp, self.K.shape[0],
+                                self.mf, self.c_std, _ptr(self.cand_hw), _ptr(self.cand_frame),
+                                _ptr(self.n_cand), _ptr(self.thr), self.cap, _ptr(self.scratch),
+                                self.sbytes, st))
+        if fit:
+            n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * self.F)
+            _lib.check(L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
+                                            _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
+                                            ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
+                                            None, _ptr(self.counter), st))
+
+    def run_detect_only(self, frames_dev):
+        self.run(frames_dev, fit=False)
+
+    def run_fit_only(self, frames_dev):
+        """Re-fit the candidates of the last detection (used to time the fit kernel alone)."""
+        n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * self.F)
+        _lib.check(self.L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
+                                             _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
+                                             ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
+                                             None, _ptr(self.counter), _stream()))
+
+    def total(self):
+        """Synchronising read of the candidate total; raises if the capacity was exceeded."""
+        n = int(self.n_cand[self.F].item())
+        if n > self.cap:
+            raise _lib.FsqError("capacity: %d candidates > cap %d; enlarge cap_per_frame" % (n, self.cap))
+        return n
+
+    def fetch(self, pinned=None):
+        """One D2H copy of the packed per-candidate results -> (n, cand_hw, cand_frame, fit, ints, n_cand)."""
+        n = self.total()
+        if pinned is not None:
+            pinned["fit"][:n].copy_(self.out_fit[:n], non_blocking=True)
+            pinned["ints"][:n].copy_(self.out_int[:n], non_blocking=True)
+            pinned["hw"][:n].copy_(self.cand_hw[:n], non_blocking=True)
+            pinned["frame"][:n].copy_(self.cand_frame[:n], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return n, pinned["hw"][:n], pinned["frame"][:n], pinned["fit"][:n], pinned["ints"][:n]
+        return (n, self.cand_hw[:n].cpu(), self.cand_frame[:n].cpu(), self.out_fit[:n].cpu(),
+                self.out_int[:n].cpu())
+
+    def pinned_buffers(self):
+        return {"fit": torch.empty((self.cap, 12), dtype=torch.float64).pin_memory(),
+                "ints": torch.empty((self.cap, 4), dtype=torch.int32).pin_memory(),
+                "hw": torch.empty((self.cap, 2), dtype=torch.int32).pin_memory(),
+                "frame": torch.empty(self.cap, dtype=torch.int32).pin_memory()}
+
+    def d2h_bytes(self, n):
+        return n * (12 * 8 + 4 * 4 + 2 * 4 + 4)

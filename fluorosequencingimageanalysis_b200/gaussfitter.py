@@ -1,0 +1,155 @@
+"""
+Drop-in mirror of the reference's ``gaussfitter`` 2-D entry points (agpy/gaussfitter.py:29-255):
+``gaussfit``, ``twodgaussian``, ``moments`` -- same signatures and return selection.  The fit
+itself (the ``mpfit`` call of gaussfitter.py:243) runs in the CUDA LM kernel of libfsq.so.
+
+What cannot be dropped in: ``mpfit`` with an arbitrary Python
+callable.  The GPU path covers what this code base uses: the 7-parameter model
+(circle=0, rotate=1, vheight=1), err=None, no fixed parameters.
+"""
+import numpy as np
+from numpy import pi
+from numpy.ma import median
+
+from . import engine
+
+
+def moments(data, circle, rotate, vheight, estimator=median, **kwargs):
+    """agpy/gaussfitter.py:29-61: (height, amplitude, x, y, width_x, width_y, rotation)
+    start values from moments; host-side argument marshalling."""
+    total = np.abs(data).sum()
+    Y, X = np.indices(data.shape)
+    y = np.argmax((X * np.abs(data)).sum(axis=1) / total)
+    x = np.argmax((Y * np.abs(data)).sum(axis=0) / total)
+    col = data[int(y), :]
+    width_x = np.sqrt(np.abs((np.arange(col.size) - y) * col).sum() / np.abs(col).sum())
+    row = data[:, int(x)]
+    width_y = np.sqrt(np.abs((np.arange(row.size) - x) * row).sum() / np.abs(row).sum())
+    width = (width_x + width_y) / 2.
+    height = estimator(data.ravel())
+    amplitude = data.max() - height
+    mylist = [amplitude, x, y]
+    if np.isnan(width_y) or np.isnan(width_x) or np.isnan(height) or np.isnan(amplitude):
+        raise ValueError("something is nan")
+    if vheight == 1:
+        mylist = [height] + mylist
+    if circle == 0:
+        mylist = mylist + [width_x, width_y]
+        if rotate == 1:
+            mylist = mylist + [0.]
+    else:
+        mylist = mylist + [width]
+    return mylist
+
+
+def twodgaussian(inpars, circle=False, rotate=True, vheight=True, shape=None):
+    """agpy/gaussfitter.py:63-140.  NOTE the third parameter is the centre along axis 1 and
+    the fourth along axis 0 of numpy.indices (gaussfitter.py:100)."""
+    inpars_old = inpars
+    inpars = list(inpars)
+    height = float(inpars.pop(0)) if vheight == 1 else float(0)
+    amplitude, center_y, center_x = float(inpars.pop(0)), float(inpars.pop(0)), float(inpars.pop(0))
+    if circle == 1:
+        width_x = width_y = float(inpars.pop(0))
+        rotate = 0
+    else:
+        width_x, width_y = float(inpars.pop(0)), float(inpars.pop(0))
+    if rotate == 1:
+        rota = pi / 180. * float(inpars.pop(0))
+        rcen_x = center_x * np.cos(rota) - center_y * np.sin(rota)
+        rcen_y = center_x * np.sin(rota) + center_y * np.cos(rota)
+    else:
+        rota = 0.
+        rcen_x, rcen_y = center_x, center_y
+    if len(inpars) > 0:
+        raise ValueError("There are still input parameters:" + str(inpars) +
+                         " and you've input: " + str(inpars_old) +
+                         " circle=%d, rotate=%d, vheight=%d" % (circle, rotate, vheight))
+
+    def rotgauss(x, y):
+        if rotate == 1:
+            xp = x * np.cos(rota) - y * np.sin(rota)
+            yp = x * np.sin(rota) + y * np.cos(rota)
+        else:
+            xp, yp = x, y
+        return height + amplitude * np.exp(-(((rcen_x - xp) / width_x) ** 2 +
+                                             ((rcen_y - yp) / width_y) ** 2) / 2.)
+    if shape is not None:
+        return rotgauss(*np.indices(shape))
+    return rotgauss
+
+
+class MpfitResult(object):
+    """The attributes of the reference's mpfit object that gaussfit callers read
+    (agpy/mpfit/mpfit.py:749-838)."""
+    _ERRMSG = {0: 'ERROR: parameters are not within PARINFO limits',
+               -16: "ERROR: parameter or function value(s) have become infinite; "
+                    "check model function for over- and underflow"}
+
+    def __init__(self, params, perror, status, niter, nfev, fnorm, dof, n_qrsolv):
+        self.params = params
+        self.perror = perror
+        self.covar = None            # not produced by the batched kernel (perror is)
+        self.status = status
+        self.niter = niter
+        self.nfev = nfev
+        self.fnorm = fnorm
+        self.dof = dof
+        self.errmsg = self._ERRMSG.get(status, '')
+        self.n_qrsolv = n_qrsolv     # extra: 0 <=> robust set
+
+
+FAITHFUL = True
+
+
+def gaussfit(data, err=None, params=(), autoderiv=True, return_all=False, circle=False,
+             fixed=np.repeat(False, 7), limitedmin=[False, False, False, False, True, True, True],
+             limitedmax=[False, False, False, False, False, False, True],
+             usemoment=np.array([], dtype='bool'),
+             minpars=np.repeat(0, 7), maxpars=[0, 0, 0, 0, 0, 0, 360],
+             rotate=1, vheight=1, quiet=True, returnmp=False,
+             returnfitimage=False, **kwargs):
+    """agpy/gaussfitter.py:142-255."""
+    data = np.asarray(data)
+    usemoment = np.array(usemoment, dtype='bool')
+    params = np.array(params, dtype='float')
+    if usemoment.any() and len(params) == len(usemoment):
+        moment = np.array(moments(data, circle, rotate, vheight, **kwargs), dtype='float')
+        params[usemoment] = moment[usemoment]
+    elif len(params) == 0:
+        params = np.array(moments(data, circle, rotate, vheight, **kwargs), dtype='float')
+    if autoderiv == 0:
+        raise ValueError("I'm sorry, I haven't implemented this feature yet.")   # gaussfitter.py:239
+    if circle or not rotate or not vheight or err is not None or np.any(np.asarray(fixed)):
+        raise NotImplementedError("the CUDA path fits the 7-parameter model (circle=0, rotate=1, "
+                                  "vheight=1, err=None, no fixed parameters) -- SURVEY.md 8(b)")
+    if len(params) != 7:
+        raise ValueError("expected 7 parameters, got %d" % len(params))
+    lmin = np.asarray(limitedmin, dtype=bool)
+    lmax = np.asarray(limitedmax, dtype=bool)
+    mn = np.asarray(minpars, dtype=float)
+    mx = np.asarray(maxpars, dtype=float)
+    for i in range(len(params)):                                             # gaussfitter.py:202-204
+        if params[i] > mx[i] and lmax[i]:
+            params[i] = mx[i]
+        if params[i] < mn[i] and lmin[i]:
+            params[i] = mn[i]
+    win = data[None].astype(np.int64) if data.dtype.kind in "iub" else data[None].astype(np.float64)
+    r = engine.gaussfit_batch(win, params[None], mn[None], mx[None], lmin[None].astype(np.uint8),
+                              lmax[None].astype(np.uint8), faithful=FAITHFUL,
+                              want_perror=bool(return_all or returnmp), want_fit_img=bool(returnfitimage))
+    p = r.params[0].cpu().numpy()
+    status = int(r.status[0].item())
+    perror = None
+    if r.perror is not None and status > 0:
+        perror = r.perror[0].cpu().numpy()
+    if returnmp:
+        returns = MpfitResult(p, perror, status, int(r.niter[0].item()), int(r.nfev[0].item()),
+                              float(r.chi2[0].item()), data.size - 7, int(r.n_qrsolv[0].item()))
+    elif return_all == 0:
+        returns = p
+    else:
+        returns = p, perror
+    if returnfitimage:
+        returns = (returns, r.fit_img[0].cpu().numpy())
+    return returns

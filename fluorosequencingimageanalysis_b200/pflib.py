@@ -1,0 +1,161 @@
+"""
+Drop-in mirror of the reference's ``pflib`` hot-path functions (same names, argument meaning,
+return layouts and error behaviour), backed by the CUDA kernels of libfsq.so.
+
+  _psf_candidates   pflib.py:217-258      find_peptides   pflib.py:284-520
+  _fit_2d_gaussian  pflib.py:180-214      illumina_s_n    pflib.py:261-281
+  image_batch / parallel_image_batch  pflib.py:883-1111 -> see sharding.py (multi-GPU partitioner)
+
+``import fluorosequencingimageanalysis_b200.pflib as pflib`` (or the sys.modules alias shown
+in INTEGRATION.md) lets flexlibrary / the basic_*_script drivers run unchanged.
+"""
+import math
+
+import numpy as np
+
+from . import engine
+from .engine import DEFAULT_CORRELATION_MATRIX
+
+default_correlation_matrix = DEFAULT_CORRELATION_MATRIX.copy()      # pflib.py:48-52
+
+#: set to False to get clean-MINPACK fits instead of reproducing the reference's qrsolv
+#: diagonal-view behaviour
+FAITHFUL = True
+
+
+def _py2_round(x):
+    """Python-2 round(): half away from zero (pflib.py:515)."""
+    x = float(x)
+    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+
+
+def _psf_candidates(image, median_filter_size=5, correlation_matrix=default_correlation_matrix,
+                    c_std=2, **kwargs):
+    """pflib.py:217-258 -> [(h, w), ...] raster order."""
+    image = np.asarray(image)
+    if image.ndim != 2:
+        raise ValueError("image must be two-dimensional")
+    det = engine.detect_batch(image, median_filter_size, correlation_matrix, c_std)
+    hw = det.cand_hw[:det.total].cpu().numpy()
+    return [(int(h), int(w)) for h, w in hw]
+
+
+def _pflib_limits(sub):
+    """Start values / limits of pflib.py:199-213 for n windows [n,5,5] (host-side argument
+    marshalling only; the kernel clamps like gaussfitter.py:202-204)."""
+    n = sub.shape[0]
+    flat = sub.reshape(n, 25)
+    mx = flat.max(axis=1).astype(np.float64)
+    p0 = np.tile(np.array([0, 0, 2.5, 2.5, 1, 1, 0], dtype=np.float64), (n, 1))
+    p0[:, 0] = np.median(flat, axis=1)
+    p0[:, 1] = mx
+    lo = np.tile(np.array([0.0, 0.0, 2.0, 2.0, 0.75, 0.75, 0.0]), (n, 1))
+    lo[:, 1] = (mx - flat.mean(axis=1)) / 3.0
+    hi = np.tile(np.array([0.0, 0.0, 3.0, 3.0, 2.0, 2.0, 360.0]), (n, 1))
+    lim_lo = np.ones((n, 7), dtype=np.uint8)
+    lim_hi = np.tile(np.array([0, 0, 1, 1, 1, 1, 1], dtype=np.uint8), (n, 1))
+    # gaussfitter.py:202-204 start clamp
+    p0 = np.where((p0 > hi) & (lim_hi != 0), hi, p0)
+    p0 = np.where((p0 < lo) & (lim_lo != 0), lo, p0)
+    return p0, lo, hi, lim_lo, lim_hi
+
+
+def _fit_2d_gaussian(subimage, implementation='agpy'):
+    """pflib.py:180-214 -> (h_0, w_0, H, A, sigma_h, sigma_w, theta, fit_img)."""
+    subimage = np.asarray(subimage)
+    assert subimage.shape[0] == 5 and subimage.shape[1] == 5
+    if implementation != 'agpy':
+        raise NotImplementedError("Currently, only agpy is supported.")
+    sub = subimage.astype(np.int64)[None] if subimage.dtype.kind in "iub" else subimage.astype(np.float64)[None]
+    p0, lo, hi, lim_lo, lim_hi = _pflib_limits(sub)
+    r = engine.gaussfit_batch(sub, p0, lo, hi, lim_lo, lim_hi, faithful=FAITHFUL, want_fit_img=True)
+    H, A, h_0, w_0, sigma_h, sigma_w, theta = (float(v) for v in r.params[0].cpu().numpy())
+    return (h_0, w_0, H, A, sigma_h, sigma_w, theta, r.fit_img[0].cpu().numpy())
+
+
+def illumina_s_n(sub_img):
+    """pflib.py:261-281."""
+    sub_img = np.asarray(sub_img)
+    if not (len(sub_img.shape) == 2 and sub_img.shape[0] == sub_img.shape[1]):
+        raise ValueError("sub_img must be square, but has shape " + str(sub_img))
+    if sub_img.shape[0] != 5:
+        raise NotImplementedError("the CUDA metrics kernel handles the 5x5 spots pflib/flexlibrary use")
+    out = engine.metrics_batch(sub_img[None], sub_img[None].astype(np.float64))
+    return float(out[0, 2].item())
+
+
+def consolidate_packed(cand_hw, fit, shape, r_2_threshold=0.7, consolidation_radius=4):
+    """R^2 gate + rival consolidation + re-key of pflib.py:466-468, 479-519 on packed arrays of
+    ONE frame.  cand_hw [n,2] raster order, fit [n,>=10] (h_0,w_0,...,r_2 at column 8).
+    Returns (keys [m,2] int, idx [m] indices into the candidate arrays) in dict-insertion order.
+    Host logic (next row 8(f)-1 moves it to the device)."""
+    if consolidation_radius < 2:
+        raise ValueError("consolidation_radius must be at least 2")          # pflib.py:431-432
+    H, W = shape
+    n = cand_hw.shape[0]
+    r2 = fit[:, engine.COL_R2]
+    keep = ~(r2 < r_2_threshold)                                              # :466 discards only when '<'
+    grid = -np.ones((H, W), dtype=np.int64)
+    order = np.nonzero(keep)[0]
+    grid[cand_hw[order, 0], cand_hw[order, 1]] = order
+    alive = keep.copy()
+    h0 = fit[:, engine.COL_H0]
+    w0 = fit[:, engine.COL_W0]
+    rad = consolidation_radius
+    rr = rad ** 2
+    for i in order:
+        if not alive[i]:
+            continue
+        h, w = int(cand_hw[i, 0]), int(cand_hw[i, 1])
+        sl = grid[max(0, h - rad - 2):min(h + rad + 3, H), max(0, w - rad - 2):min(w + rad + 3, W)]
+        js = sl[sl >= 0]                                                      # raster order of (h_d, w_d)
+        for j in js:
+            if j == i or not alive[j]:
+                continue
+            if (h0[i] - h0[j]) ** 2 + (w0[i] - w0[j]) ** 2 > rr:
+                continue
+            if r2[i] > r2[j]:                                                 # :508
+                alive[j] = False
+                grid[cand_hw[j, 0], cand_hw[j, 1]] = -1
+            else:
+                alive[i] = False
+                grid[h, w] = -1
+                break
+    idx = np.nonzero(alive)[0]
+    # re-key (:514-519): delete + setdefault moves an entry to the END of the dict
+    bins = {}
+    for i in idx:
+        bins[(int(cand_hw[i, 0]), int(cand_hw[i, 1]))] = int(i)
+    for (h, w), i in list(bins.items()):
+        k = (int(_py2_round(h0[i])), int(_py2_round(w0[i])))
+        if k[0] != h or k[1] != w:
+            del bins[(h, w)]
+            assert k not in bins                                              # :518
+            bins.setdefault(k, i)
+    keys = np.array(list(bins.keys()), dtype=np.int64).reshape(-1, 2)
+    return keys, np.array(list(bins.values()), dtype=np.int64)
+
+
+def find_peptides(image, median_filter_size=5, correlation_matrix=default_correlation_matrix,
+                  candidate_pixels=None, c_std=2, r_2_threshold=0.7, consolidation_radius=4,
+                  fit_type='gauss', N_iter=10 ** 3):
+    """pflib.py:284-520 -> {(h, w): (h_0, w_0, H, A, sigma_h, sigma_w, theta, sub_img, fit_img,
+    rmse, r_2, s_n)} with sub_img 5x5 int64 and fit_img 5x5 float64."""
+    if consolidation_radius < 2:
+        raise ValueError("consolidation_radius must be at least 2")
+    if fit_type != 'gauss':
+        raise NotImplementedError("fit_type='monte_carlo' (pflib.py:117-177) is not part of the CUDA hot path")
+    image = np.asarray(image)
+    res = engine.find_peptides_batch(image, median_filter_size, correlation_matrix, c_std,
+                                     faithful=FAITHFUL, want_fit_img=True)
+    keys, idx = consolidate_packed(res.cand_hw, res.fit, image.shape, r_2_threshold, consolidation_radius)
+    out = {}
+    for (kh, kw), i in zip(keys, idx):
+        h, w = int(res.cand_hw[i, 0]), int(res.cand_hw[i, 1])
+        f = res.fit[i]
+        sub_img = image[h - 2:h + 3, w - 2:w + 3].astype(np.int64)            # pflib.py:443
+        fit_img = res.fit_img[i].reshape(5, 5).copy()
+        out[(int(kh), int(kw))] = (float(f[0]), float(f[1]), float(f[2]), float(f[3]), float(f[4]),
+                                   float(f[5]), float(f[6]), sub_img, fit_img, float(f[7]), float(f[8]),
+                                   float(f[9]))
+    return out

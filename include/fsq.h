@@ -1,0 +1,173 @@
+/*
+ * fsq.h -- C-ABI of libfsq.so: the B200 (sm_100a) implementation of the per-field spot hot
+ * path of marcottelab/FluorosequencingImageAnalysis.
+ *
+ * Every entry point replaces the inside of one reference function (cited per function as
+ * file:line under /root/reference); the reference-side binding is the ctypes stub shown in
+ * INTEGRATION.md.  Plain pointers and sizes only: all data pointers are DEVICE pointers
+ * unless the name ends in _host; the caller (Python/torch) owns every buffer, inputs and
+ * outputs, including scratch.  All launches are asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = legacy default stream).  The library keeps no mutable global state
+ * besides a thread-local error string and is safe to call from N threads/processes each
+ * bound to one GPU.
+ *
+ * Return convention: 0 success; <0 failure (see FSQ_E_*); text via fsq_last_error().
+ * Per-fit failures are NOT errors: they are `status` values with mpfit's meaning
+ * (agpy/mpfit/mpfit.py:754-790): 0 bad input, 1..4 converged, 5 maxiter, 6..8 tolerance too
+ * small, -16 non-finite.
+ */
+#ifndef FSQ_H_
+#define FSQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSQ_VERSION 100            /* 0.1.0 */
+
+#define FSQ_OK          0
+#define FSQ_E_ARG      -1          /* bad argument (NULL pointer, even kernel size, unsupported dtype ...) */
+#define FSQ_E_CAPACITY -2          /* output capacity too small; required count is written where documented */
+#define FSQ_E_CUDA     -3          /* a CUDA runtime call failed */
+#define FSQ_E_RANGE    -4          /* data outside the exact-arithmetic range of the kernels */
+
+/* pixel dtype codes for frame / window inputs */
+#define FSQ_U8   0
+#define FSQ_U16  1
+#define FSQ_I16  2
+#define FSQ_I32  3
+#define FSQ_F64  4                 /* windows only (gaussfit on float data) */
+#define FSQ_I64  5                 /* windows only (pflib passes int64 sub-images) */
+
+int         fsq_version(void);
+const char* fsq_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Candidate detection -- replaces pflib._psf_candidates (pflib.py:217-258) for a batch of
+ * frames:  int64 cast -> s x s median background removal (scipy 'reflect' borders, rank
+ * s*s/2) -> k x k integer correlation (zero padded) -> clamp >= 0 -> per-frame threshold
+ * mean + c_std*std over ALL pixels -> every pixel >= threshold with a 2-px border excluded,
+ * raster order within a frame, frames in order.
+ *
+ *  frames      [n_frames, H, W] pixels of `dtype_code` (FSQ_U8/U16/I16/I32), contiguous
+ *  K_host      HOST pointer, [ksize*ksize] int64 correlation template, ksize odd, <= 9
+ *  mf_size     median filter side, 1..9
+ *  c_std       threshold coefficient
+ *  cand_hw     out [cap, 2] int32 (h, w)
+ *  cand_frame  out [cap] int32 frame index of each candidate
+ *  n_cand      out [n_frames + 1] int64: per-frame counts, then the total in the last slot
+ *  thr         out [n_frames] float64 thresholds
+ *  cap         capacity of cand_hw / cand_frame in candidates; candidates beyond cap are
+ *              dropped (the caller compares n_cand[n_frames] with cap after synchronising and
+ *              re-launches with a larger buffer -- that is the FSQ_E_CAPACITY protocol, made
+ *              asynchronous)
+ *  scratch     device scratch of at least fsq_detect_scratch_bytes(n_frames, H, W) bytes
+ * ------------------------------------------------------------------------------------------ */
+int64_t fsq_detect_scratch_bytes(int n_frames, int H, int W);
+
+int fsq_detect(const void* frames, int dtype_code, int n_frames, int H, int W,
+               const int64_t* K_host, int ksize, int mf_size, double c_std,
+               int32_t* cand_hw, int32_t* cand_frame, int64_t* n_cand, double* thr,
+               int64_t cap, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Synchronises `stream` and reports FSQ_E_RANGE when the last fsq_detect on this scratch met
+ * data outside the exact-arithmetic range (correlation value >= 2^41, or a threshold beyond
+ * the saturated uint32 correlation scratch, i.e. > 2^32). */
+int fsq_detect_flags(const void* scratch, int n_frames, int H, int W, void* stream);
+
+/* Optional outputs of the detection intermediates (tests / debugging): the clamped
+ * correlation map saturated to uint32 as stored in scratch, [n_frames, H, W]. */
+int fsq_detect_copy_cm32(const void* scratch, int n_frames, int H, int W, uint32_t* cm32_out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Levenberg-Marquardt options -- the keyword arguments of class mpfit
+ * (agpy/mpfit/mpfit.py:600-605); gaussfit leaves them all at their defaults.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fsq_lm_opts {
+    double ftol;        /* 1e-10 */
+    double xtol;        /* 1e-10 */
+    double gtol;        /* 1e-10 */
+    double factor;      /* 100   */
+    int32_t maxiter;    /* 200   */
+    int32_t faithful;   /* 1: reproduce the reference's qrsolv diagonal-view behaviour
+                              (mpfit.py:1915,1956,1976-1977); 0: clean MINPACK            */
+    int32_t want_perror;/* 1: compute covariance -> perror (mpfit.py:1361-1388)           */
+    int32_t reserved;
+} fsq_lm_opts;
+
+void fsq_lm_default_opts(fsq_lm_opts* o);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched 2-D Gaussian fit -- replaces gaussfitter.gaussfit (agpy/gaussfitter.py:142-255)
+ * -> class mpfit (agpy/mpfit/mpfit.py:600-1388) for the 7-parameter rotated elliptical
+ * Gaussian (height, amplitude, p2, p3, width_x, width_y, rota_deg) with err=None.
+ *
+ *  windows     [n, win, win] of `dtype_code` (FSQ_F64, FSQ_I64, FSQ_U16, FSQ_I32), win <= 11
+ *  p0          [n, 7] float64 start values (already clamped like gaussfitter.py:202-204)
+ *  lo, hi      [n, 7] float64 limits;  lim_lo, lim_hi [n, 7] uint8 "limited" flags
+ *  params      out [n, 7]   perror out [n, 7] (may be NULL unless want_perror)
+ *  status/niter/nfev out [n] int32;  chi2 out [n] (= mpfit .fnorm)
+ *  n_qrsolv    out [n] int32 number of qrsolv calls (0 <=> robust set); may be NULL
+ *  fit_img     out [n, win, win] float64 model at the final parameters; may be NULL
+ * ------------------------------------------------------------------------------------------ */
+int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n, int win,
+                       const double* p0, const double* lo, const double* hi,
+                       const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
+                       double* params, double* perror, int32_t* status, int32_t* niter,
+                       int32_t* nfev, double* chi2, int32_t* n_qrsolv, double* fit_img,
+                       int64_t* work_counter, void* stream);
+
+/* Same fit with a per-trial-step trace for the first trace_n windows (tests / debugging).
+ * trace is [trace_n, trace_steps, 20] float64, zero-initialised by the caller; record 0 of a
+ * window holds the number of records written in [0]; record k >= 1 = (niter, accepted, status,
+ * fnorm, fnorm1, delta, par, ratio, alpha, pnorm, xnew[0..6], n_qrsolv, actred, prered). */
+int fsq_gaussfit_batch_trace(const void* windows, int dtype_code, int64_t n, int win,
+                             const double* p0, const double* lo, const double* hi,
+                             const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
+                             double* params, int32_t* status, int32_t* niter, int32_t* nfev,
+                             double* chi2, int32_t* n_qrsolv, double* trace, int trace_steps,
+                             int64_t trace_n, int64_t* work_counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fit every candidate of a batch of frames the way pflib.find_peptides does
+ * (pflib.py:441-477 -> _fit_2d_gaussian pflib.py:180-214): 5x5 window sliced from the RAW
+ * frame around (h, w); start (median, max, 2.5, 2.5, 1, 1, 0); limits
+ * [0,inf) x [(max-mean)/3, inf) x [2,3]^2 x [0.75,2]^2 x [0,360]; then the fit-quality
+ * metrics of pflib.py:461-473 fused at the end.
+ *
+ *  out_fit     [n, 12] float64: h_0, w_0, H, A, sigma_h, sigma_w, theta (image coordinates,
+ *              pflib.py:461), rmse, r_2, s_n, chi2, (reserved)
+ *  out_int     [n, 4] int32: status, niter, nfev, n_qrsolv
+ *  fit_img     [n, 25] float64 or NULL
+ *  work_counter device int64 used as the work-queue head; the call zeroes it
+ * ------------------------------------------------------------------------------------------ */
+int fsq_fit_candidates(const void* frames, int dtype_code, int n_frames, int H, int W,
+                       const int32_t* cand_hw, const int32_t* cand_frame, int64_t n,
+                       const int64_t* n_dev /* optional device count (n_cand total); NULL = use n */,
+                       const fsq_lm_opts* opts, double* out_fit, int32_t* out_int,
+                       double* fit_img, int64_t* work_counter, void* stream);
+
+/* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
+ * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
+int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Photometry on spots -- flexlibrary.Spot.photometry family (flexlibrary.py:160-210, 264-284)
+ *  method 0: simple (sum of size x size), 1: mexican_hat (radius, brim), 2: maximum (radius, top=1)
+ *  spots_hw [n,2] int32, spot_frame [n] int32, out [n] float64
+ * ------------------------------------------------------------------------------------------ */
+int fsq_photometry(const void* frames, int dtype_code, int n_frames, int H, int W,
+                   const int32_t* spots_hw, const int32_t* spot_frame, int64_t n,
+                   int method, int radius, int brim, double* out, void* stream);
+
+/* FP64/FP32 FMA micro-benchmark used for the roofline denominator (bench.py); returns
+ * achieved FLOP/s through *flops_out (host pointer). */
+int fsq_fma_peak(int fp64, double* flops_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSQ_H_ */

@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""
+TEST INFRASTRUCTURE.  Perturbation-stability of the reference's fits.
+
+Finding (DESIGN.md "Parity"): in the pflib call the rotation angle starts pegged on its lower
+bound with width_x == width_y, so its finite-difference Jacobian column is pure rounding noise
+(a few ulps of exp()).  The very first LM step scales ALL parameters by
+alpha = 360/|noise-driven theta step| (mpfit.py:1192-1202), so the trajectory -- and, because
+55 % of the reference's exits are premature and the box limits create several end points, the
+RESULT -- of most fits depends on the last bit of libm's exp().  Any implementation whose exp()
+is not bit-identical to the numpy build that produced the goldens (including the reference
+itself on another machine) therefore differs on those fits.
+
+This script measures that on the oracle: it re-runs every golden fit with the model's exp()
+perturbed by +1 ulp on a deterministic pseudo-random half of its values (K different hashes),
+and marks a fit STABLE when every perturbed run reproduces the unperturbed answer
+(H, A, centre, sorted widths; status too in the faithful flavour).  The flags are stored next
+to the goldens (tests/golden/stable5_seed0.npz, stable11_seed0.npz) and define the set on
+which the CUDA path must reproduce the reference per fit.
+
+    python oracle/stability.py [--procs 8] [--k 3]
+"""
+import argparse
+import multiprocessing
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import lm_oracle, pflib_oracle as po              # noqa: E402
+from fluorosequencingimageanalysis_b200 import synth          # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gauss2d_perturbed(p, shape, bit):
+    """pflib_oracle.gauss2d with exp() nudged by one ulp where hash bit `bit` of the value is set."""
+    height, amplitude, center_y, center_x, width_x, width_y = [float(v) for v in p[:6]]
+    rota = np.pi / 180. * float(p[6])
+    rcen_x = center_x * np.cos(rota) - center_y * np.sin(rota)
+    rcen_y = center_x * np.sin(rota) + center_y * np.cos(rota)
+    x, y = np.indices(shape)
+    xp = x * np.cos(rota) - y * np.sin(rota)
+    yp = x * np.sin(rota) + y * np.cos(rota)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = np.exp(-(((rcen_x - xp) / width_x) ** 2 + ((rcen_y - yp) / width_y) ** 2) / 2.)
+    bits = e.view(np.int64)
+    e = np.where((bits >> bit) & 1, np.nextafter(e, 2.0), e)
+    return height + amplitude * e
+
+
+def agree(P, Q, tol=1e-4, ctol=1e-3):
+    """Symmetry-aware parameter agreement: H, A relative, centres absolute, widths as a set
+    ((wx, wy, theta) == (wy, wx, theta + 90) describe the same ellipse)."""
+    P = np.atleast_2d(P)
+    Q = np.atleast_2d(Q)
+    rel = lambda a, b: np.abs(a - b) / np.maximum(np.abs(b), 1e-300)     # noqa: E731
+    ok = (rel(P[:, 0], Q[:, 0]) < tol) & (rel(P[:, 1], Q[:, 1]) < tol)
+    ok &= (np.abs(P[:, 2] - Q[:, 2]) < ctol) & (np.abs(P[:, 3] - Q[:, 3]) < ctol)
+    sp, sq = np.sort(P[:, 4:6], axis=1), np.sort(Q[:, 4:6], axis=1)
+    ok &= (rel(sp[:, 0], sq[:, 0]) < tol) & (rel(sp[:, 1], sq[:, 1]) < tol)
+    return ok
+
+
+def _run(args):
+    data, start, lims, bit, faithful = args
+    lmin, lmax, mn, mx = lims
+
+    def resid(p):
+        return np.ravel(data - gauss2d_perturbed(p, data.shape, bit))
+    res = lm_oracle.lm_solve(resid, np.array(start, dtype=float), np.asarray(lmin, dtype=bool),
+                             np.asarray(lmax, dtype=bool), np.asarray(mn, dtype=float),
+                             np.asarray(mx, dtype=float), faithful=faithful)
+    return res.params, res.status, res.fnorm
+
+
+def ensemble(pool, jobs, K):
+    out = []
+    for k in range(K):
+        bit = 3 + 2 * k
+        rows = pool.map(_run, [(d, s, l, bit, f) for (d, s, l, f) in jobs], chunksize=16)
+        out.append((np.array([r[0] for r in rows]), np.array([r[1] for r in rows]),
+                    np.array([r[2] for r in rows])))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--k", type=int, default=3)
+    a = ap.parse_args()
+    g5 = dict(np.load(os.path.join(GOLD, "fits5_seed0.npz")))
+    img = synth.synth_frame(0)
+    subs = [img[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in g5["cands"]]
+    with multiprocessing.Pool(a.procs) as pool:
+        res = {}
+        for faithful, key in ((True, "ref"), (False, "clean")):
+            jobs = []
+            for s in subs:
+                p, lmin, lmax, mn, mx = po.pflib_fit_args(s)
+                jobs.append((s, p, (lmin, lmax, mn, mx), faithful))
+            ens = ensemble(pool, jobs, a.k)
+            base_p, base_s = g5[key + "_params"], g5[key + "_status"]
+            stable = np.ones(len(subs), dtype=bool)
+            for P, S, _ in ens:
+                stable &= agree(P, base_p)
+                if faithful:
+                    stable &= (S == base_s)
+            res["stable_" + key] = stable
+            res["ens_params_" + key] = np.stack([e[0] for e in ens])
+            res["ens_status_" + key] = np.stack([e[1] for e in ens])
+            print("5x5 %s: stable %d of %d (%.1f %%)" % (key, stable.sum(), len(stable), 100 * stable.mean()))
+        np.savez_compressed(os.path.join(GOLD, "stable5_seed0.npz"), k=a.k, **res)
+
+        g11 = dict(np.load(os.path.join(GOLD, "fits11_seed0.npz")))
+        res = {}
+        lims = (po.GAUSSFIT_DEFAULT_LIMITEDMIN, po.GAUSSFIT_DEFAULT_LIMITEDMAX,
+                po.GAUSSFIT_DEFAULT_MINPARS, po.GAUSSFIT_DEFAULT_MAXPARS)
+        for faithful, key in ((True, "ref"), (False, "clean")):
+            jobs = [(w, p0, lims, faithful) for w, p0 in zip(g11["windows"], g11["p0"])]
+            ens = ensemble(pool, jobs, a.k)
+            stable = np.ones(len(jobs), dtype=bool)
+            for P, S, _ in ens:
+                stable &= agree(P, g11[key + "_params"])
+                if faithful:
+                    stable &= (S == g11[key + "_status"])
+            res["stable_" + key] = stable
+            print("11x11 %s: stable %d of %d" % (key, stable.sum(), len(stable)))
+        np.savez_compressed(os.path.join(GOLD, "stable11_seed0.npz"), k=a.k, **res)
+
+
+if __name__ == "__main__":
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    main()
