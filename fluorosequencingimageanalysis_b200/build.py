@@ -20,6 +20,10 @@ SOURCES = ["fsq_api.cu", "fsq_detect.cu", "fsq_lmfit.cu"]
 HEADERS = ["fsq_common.cuh", os.path.join("..", "..", "include", "fsq.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# per-file extras.  The reference-faithful MINPACK kernel is compiled without implicit FMA
+# contraction: every fused operation in it is an explicit fma(), so its arithmetic is fixed by
+# the source (two template instantiations give bit-identical fits) -- DESIGN.md "Parity".
+EXTRA_FLAGS = {"fsq_lmfit.cu": ["-fmad=false"]}
 
 
 def _nvcc():
@@ -34,7 +38,7 @@ def _digest():
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
     return h.hexdigest()
 
 
@@ -48,7 +52,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

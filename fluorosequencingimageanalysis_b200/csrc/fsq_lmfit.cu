@@ -72,14 +72,19 @@ __device__ __forceinline__ double enorm7(const double* v) {
 template <int S>
 struct Rot { double cs, sn; double xp[S], yp[S]; };
 
+// The model is evaluated with the reference's exact operation sequence, every operation
+// individually rounded (no FMA contraction, true divisions): the rotation column of the
+// finite-difference Jacobian is pure rounding noise at the pflib start point (theta pegged at 0
+// with width_x == width_y), so the first LM step -- and with it the end point of most
+// non-stable fits -- depends on the last bit of every intermediate (DESIGN.md "Parity").
 template <int S>
 __device__ __forceinline__ void make_rot(double theta_deg, const double (&px)[S], const double (&py)[S], Rot<S>& r) {
-    const double rota = FSQ_DEG2RAD * theta_deg;          // gaussfitter.py:115
+    const double rota = __dmul_rn(FSQ_DEG2RAD, theta_deg);   // gaussfitter.py:115  pi/180. * rota
     sincos(rota, &r.sn, &r.cs);
 #pragma unroll
     for (int s = 0; s < S; ++s) {                         // gaussfitter.py:128-129
-        r.xp[s] = px[s] * r.cs - py[s] * r.sn;
-        r.yp[s] = px[s] * r.sn + py[s] * r.cs;
+        r.xp[s] = __dsub_rn(__dmul_rn(px[s], r.cs), __dmul_rn(py[s], r.sn));
+        r.yp[s] = __dadd_rn(__dmul_rn(px[s], r.sn), __dmul_rn(py[s], r.cs));
     }
 }
 
@@ -87,15 +92,19 @@ __device__ __forceinline__ void make_rot(double theta_deg, const double (&px)[S]
 // p[2] is popped as center_y, p[3] as center_x (gaussfitter.py:100)
 template <int S>
 __device__ __forceinline__ void eval_E(const double (&p)[NP], const Rot<S>& r, double (&E)[S]) {
-    const double rcx = p[3] * r.cs - p[2] * r.sn;
-    const double rcy = p[3] * r.sn + p[2] * r.cs;
-    const double iwx = 1.0 / p[4], iwy = 1.0 / p[5];
+    const double rcx = __dsub_rn(__dmul_rn(p[3], r.cs), __dmul_rn(p[2], r.sn));
+    const double rcy = __dadd_rn(__dmul_rn(p[3], r.sn), __dmul_rn(p[2], r.cs));
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const double a = (rcx - r.xp[s]) * iwx;
-        const double b = (rcy - r.yp[s]) * iwy;
-        E[s] = exp(-0.5 * (a * a + b * b));
+        const double a = __ddiv_rn(__dsub_rn(rcx, r.xp[s]), p[4]);
+        const double b = __ddiv_rn(__dsub_rn(rcy, r.yp[s]), p[5]);
+        E[s] = exp(__dmul_rn(-0.5, __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))));
     }
+}
+
+// height + amplitude * E, then data - model (gaussfitter.py:133, :214), separately rounded
+__device__ __forceinline__ double model_of(double height, double amplitude, double e) {
+    return __dadd_rn(height, __dmul_rn(amplitude, e));
 }
 
 __device__ __forceinline__ double load_as_double(const void* base, int dtype, size_t off) {
@@ -454,7 +463,7 @@ lmfit_kernel(const LmArgs a) {
                 double ss = 0.0;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    fv[s] = valid[s] ? dat[s] - (p[0] + p[1] * E[s]) : 0.0;
+                    fv[s] = valid[s] ? __dsub_rn(dat[s], model_of(p[0], p[1], E[s])) : 0.0;
                     ss = fma(fv[s], fv[s], ss);
                 }
                 fnorm = sqrt(group_sum<G>(ss, gmask));
@@ -476,7 +485,6 @@ lmfit_kernel(const LmArgs a) {
                 if (h == 0.0) h = FSQ_SQRT_MACHEP;
                 if (((qul >> j) & 1u) && (xj > st.ulim[j] - h)) h = -h;
                 const double xph = xj + h;
-                const double hinv = 1.0 / h;
                 double Ep[S];
                 if (j >= 2) {
                     double q[NP];
@@ -494,11 +502,11 @@ lmfit_kernel(const LmArgs a) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double gm;
-                    if (j == 0) gm = xph + p[1] * E[s];
-                    else if (j == 1) gm = p[0] + xph * E[s];
-                    else gm = p[0] + p[1] * Ep[s];
-                    const double fp_ = valid[s] ? dat[s] - gm : 0.0;
-                    J[s][j] = (fp_ - fv[s]) * hinv;
+                    if (j == 0) gm = model_of(xph, p[1], E[s]);
+                    else if (j == 1) gm = model_of(p[0], xph, E[s]);
+                    else gm = model_of(p[0], p[1], Ep[s]);
+                    const double fp_ = valid[s] ? __dsub_rn(dat[s], gm) : 0.0;
+                    J[s][j] = __ddiv_rn(__dsub_rn(fp_, fv[s]), h);              // mpfit.py:1599
                 }
             }
             nfev += NP;
@@ -751,7 +759,7 @@ lmfit_kernel(const LmArgs a) {
                 double ss = 0.0;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    f1[s] = valid[s] ? dat[s] - (pt[0] + pt[1] * E1[s]) : 0.0;
+                    f1[s] = valid[s] ? __dsub_rn(dat[s], model_of(pt[0], pt[1], E1[s])) : 0.0;
                     ss = fma(f1[s], f1[s], ss);
                 }
                 fnorm1 = sqrt(group_sum<G>(ss, gmask));
@@ -845,7 +853,7 @@ lmfit_kernel(const LmArgs a) {
             for (int j = 0; j < NP; ++j) pf[j] = st.x[j];
             double gimg[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) gimg[s] = pf[0] + pf[1] * E[s];     // gaussfitter.py:253
+            for (int s = 0; s < S; ++s) gimg[s] = model_of(pf[0], pf[1], E[s]);   // gaussfitter.py:253
             const bool want_pe = (a.o.want_perror != 0) && (PFLIB ? false : (a.perror != nullptr));
             if (want_pe) {
                 if (status > 0) covar_perror(st, perm, st.lw1);

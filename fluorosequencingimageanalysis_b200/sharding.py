@@ -49,6 +49,8 @@ def balanced_field_blocks(cand_counts_per_field, world_size):
     for r in range(1, world_size):
         target = total * r / world_size
         k = int(np.searchsorted(cs, target, side="left"))
+        if k > 0 and k <= n and (target - cs[k - 1]) <= (cs[min(k, n)] - target):
+            k -= 1                                    # nearer prefix sum
         k = min(max(k, bounds[-1]), n)
         bounds.append(k)
     bounds.append(n)

@@ -109,8 +109,11 @@ def main():
                 if faithful:
                     stable &= (S == base_s)
             res["stable_" + key] = stable
-            res["ens_params_" + key] = np.stack([e[0] for e in ens])
-            res["ens_status_" + key] = np.stack([e[1] for e in ens])
+            # float32 is ample for the 1e-4 agreement test and keeps the fixture small
+            res["ens_params_" + key] = np.stack([e[0] for e in ens]).astype(np.float32)
+            res["ens_status_" + key] = np.stack([e[1] for e in ens]).astype(np.int8)
+            res["ens_agree_" + key] = np.stack([agree(e[0], base_p) & ((e[1] == base_s) if faithful else True)
+                                                for e in ens])
             print("5x5 %s: stable %d of %d (%.1f %%)" % (key, stable.sum(), len(stable), 100 * stable.mean()))
         np.savez_compressed(os.path.join(GOLD, "stable5_seed0.npz"), k=a.k, **res)
 
@@ -127,6 +130,9 @@ def main():
                 if faithful:
                     stable &= (S == g11[key + "_status"])
             res["stable_" + key] = stable
+            res["ens_agree_" + key] = np.stack([agree(e[0], g11[key + "_params"]) &
+                                                ((e[1] == g11[key + "_status"]) if faithful else True)
+                                                for e in ens])
             print("11x11 %s: stable %d of %d" % (key, stable.sum(), len(stable)))
         np.savez_compressed(os.path.join(GOLD, "stable11_seed0.npz"), k=a.k, **res)
 

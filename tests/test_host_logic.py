@@ -1,0 +1,198 @@
+"""CPU: host-side logic of the drop-in modules (argument marshalling, consolidation / re-key,
+partitioner) against the oracle and the reference-generated goldens; the median selection
+network of the detection kernel proved by the 0-1 principle; the N>1 path on gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from fluorosequencingimageanalysis_b200 import gaussfitter, pflib, sharding, synth, engine
+from oracle import pflib_oracle as po
+
+
+# ------------------------------------------------------------------ median network (0-1 principle)
+def test_median25_network_is_a_median():
+    """A comparator network selects rank 12 of 25 for ALL inputs iff it does for all 2^25
+    0/1 inputs.  The network is parsed from the CUDA source, so the test checks what ships."""
+    src = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_detect.cu")).read()
+    body = src[src.index("__device__ __forceinline__ int median25"):src.index("#undef FSQ_CE")]
+    ces = [(int(a), int(b)) for a, b in re.findall(r"FSQ_CE\((\d+),\s*(\d+)\)", body)]
+    assert len(ces) == 99
+    assert "return p[12]" in body
+    chunk = 1 << 21
+    for base in range(0, 1 << 25, chunk):
+        v = np.arange(base, base + chunk, dtype=np.uint32)
+        w = [((v >> i) & 1).astype(np.uint8) for i in range(25)]
+        ones = np.zeros(chunk, dtype=np.uint8)
+        for x in w:
+            ones += x
+        for a, b in ces:
+            lo, hi = w[a] & w[b], w[a] | w[b]
+            w[a], w[b] = lo, hi
+        assert np.array_equal(w[12], (ones >= 13).astype(np.uint8))     # 13th smallest is 1 iff >= 13 ones
+
+
+# ------------------------------------------------------------------ argument marshalling
+def test_pflib_limits_match_reference_call():
+    img = synth.synth_frame(5, H=64, W=64, n_spots=12)
+    subs = np.stack([img[h:h + 5, w:w + 5] for h, w in ((3, 4), (20, 31), (40, 9), (55, 55))]).astype(np.int64)
+    p0, lo, hi, lim_lo, lim_hi = pflib._pflib_limits(subs)
+    for i, s in enumerate(subs):
+        p, lmin, lmax, mn, mx = po.pflib_fit_args(s)              # pflib.py:199-213
+        p = np.array(p, dtype=float)
+        p = np.where((p > mx) & np.array(lmax), mx, p)            # gaussfitter.py:202-204
+        p = np.where((p < mn) & np.array(lmin), mn, p)
+        assert np.array_equal(p0[i], p)
+        assert np.array_equal(lo[i], mn) and np.array_equal(hi[i], mx)
+        assert lim_lo[i].astype(bool).tolist() == lmin and lim_hi[i].astype(bool).tolist() == lmax
+
+
+def test_moments_and_model_match_oracle():
+    g = golden("fits11_seed0.npz")
+    for i in (0, 5, 77):
+        w = g["windows"][i]
+        assert np.array_equal(np.array(gaussfitter.moments(w, 0, 1, 1), dtype=float), g["p0"][i])
+        assert np.array_equal(np.array(po.moments(w), dtype=float), g["p0"][i])
+    p = [83.8, 1988.1, 2.68, 2.31, 1.127, 1.126, 33.0]
+    assert np.array_equal(gaussfitter.twodgaussian(p, shape=(5, 5)), po.gauss2d(p, (5, 5)))
+    assert np.array_equal(gaussfitter.twodgaussian(p)(*np.indices((7, 9))), po.gauss2d(p, (7, 9)))
+    with pytest.raises(ValueError):
+        gaussfitter.twodgaussian(p + [1.0], shape=(5, 5))         # gaussfitter.py:120-123
+    with pytest.raises(ValueError):
+        gaussfitter.moments(np.full((5, 5), np.nan), 0, 1, 1)     # gaussfitter.py:49-50
+
+
+def test_reference_error_behaviour_before_any_gpu_work():
+    with pytest.raises(ValueError, match="consolidation_radius"):
+        pflib.find_peptides(np.zeros((16, 16), dtype=np.uint16), consolidation_radius=1)   # pflib.py:431-432
+    with pytest.raises(AssertionError):
+        pflib._fit_2d_gaussian(np.zeros((7, 7)))                  # pflib.py:193
+    with pytest.raises(ValueError, match="square"):
+        pflib.illumina_s_n(np.zeros((5, 4)))                      # pflib.py:274-276
+    with pytest.raises(ValueError, match="odd"):
+        engine._check_kernel(np.ones((4, 4), dtype=int))          # pflib.py:236-239
+    with pytest.raises(ValueError, match="odd"):
+        engine._check_kernel(np.ones((3, 5), dtype=int))
+    with pytest.raises(ValueError, match="haven't implemented"):
+        gaussfitter.gaussfit(np.ones((5, 5)), autoderiv=0)        # gaussfitter.py:239
+    assert pflib._py2_round(2.5) == 3 and pflib._py2_round(3.5) == 4 and pflib._py2_round(0.49999) == 0
+
+
+# ------------------------------------------------------------------ consolidation / re-key
+def _packed_from_golden(g):
+    cands = g["cands"]
+    P = g["ref_params"]
+    fit = np.zeros((len(cands), 12))
+    fit[:, 0] = P[:, 2] + cands[:, 0] - 2.5                       # pflib.py:461
+    fit[:, 1] = P[:, 3] + cands[:, 1] - 2.5
+    fit[:, 2], fit[:, 3], fit[:, 4], fit[:, 5], fit[:, 6] = P[:, 0], P[:, 1], P[:, 4], P[:, 5], P[:, 6]
+    fit[:, 7], fit[:, 8], fit[:, 9] = g["rmse"], g["r_2"], g["s_n"]
+    return cands, fit
+
+
+def test_consolidate_packed_reproduces_reference_psf_keys(fits5):
+    """Fed with the REFERENCE's own per-candidate fits, the packed consolidation + re-key must
+    return exactly the reference's final PSF dictionary keys (pflib.py:479-519); the
+    insertion order is pinned by test_consolidate_packed_equals_oracle_dict_logic_random and
+    the pipeline_small golden."""
+    cands, fit = _packed_from_golden(fits5)
+    keys, idx = pflib.consolidate_packed(cands, fit, (512, 512))
+    order = np.lexsort((keys[:, 1], keys[:, 0]))                  # the golden stores the keys sorted
+    assert np.array_equal(keys[order], fits5["final_keys"])
+    assert np.array_equal(fit[idx[order], 0], fits5["final_h0"])
+    assert np.array_equal(fit[idx[order], 1], fits5["final_w0"])
+
+
+def test_consolidate_packed_equals_oracle_dict_logic_random():
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        H = W = 60
+        n = 150
+        hw = np.unique(np.stack([rng.integers(2, H - 2, n), rng.integers(2, W - 2, n)], axis=1), axis=0)
+        n = len(hw)
+        fit = np.zeros((n, 12))
+        fit[:, 0] = hw[:, 0] + rng.uniform(-0.5, 0.5, n).round(1)       # many exact .5 ties
+        fit[:, 1] = hw[:, 1] + rng.uniform(-0.5, 0.5, n).round(1)
+        fit[:, 8] = rng.choice([0.5, 0.71, 0.8, 0.9, 0.95], n)          # ties in r_2 too
+        radius = int(rng.integers(2, 6))
+        d = {}
+        for i in range(n):
+            if fit[i, 8] < 0.7:
+                continue
+            d[(int(hw[i, 0]), int(hw[i, 1]))] = (fit[i, 0], fit[i, 1], 0, 0, 0, 0, 0, None, None, 0, fit[i, 8], 0, i)
+        try:
+            want = po.consolidate(d, (H, W), radius)
+        except AssertionError:
+            with pytest.raises(AssertionError):
+                pflib.consolidate_packed(hw, fit, (H, W), 0.7, radius)
+            continue
+        keys, idx = pflib.consolidate_packed(hw, fit, (H, W), 0.7, radius)
+        assert [tuple(k) for k in keys.tolist()] == list(want.keys())
+        assert idx.tolist() == [v[12] for v in want.values()]
+
+
+# ------------------------------------------------------------------ partitioner
+def test_balance_by_count_follows_reference_greedy():
+    counts = [50, 10, 40, 10, 30, 20]
+    parts = sharding.balance_by_count(counts, 2)
+    # pflib.py:1056-1069: sorted descending, popped from the end (smallest first), emptiest partition
+    # stable descending sort -> [0, 2, 4, 5, 1, 3]; pops 3, 1, 5, 4, 2, 0
+    assert parts == [[3, 5, 2], [1, 4, 0]]
+    assert sorted(i for p in parts for i in p) == list(range(6))
+    with pytest.raises(ValueError):
+        sharding.balance_by_count(counts, 0)
+
+
+def test_field_blocks_cover_and_balance():
+    for n, ws in ((8000, 8), (100, 8), (7, 4), (3, 8)):
+        blocks = [sharding.field_block(n, ws, r) for r in range(ws)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(ws - 1))
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    c = np.r_[np.full(10, 100), np.full(10, 300)]
+    bl = sharding.balanced_field_blocks(c, 2)
+    assert bl[0][0] == 0 and bl[-1][1] == 20 and bl[0][1] == bl[1][0]
+    tot = [c[a:b].sum() for a, b in bl]
+    assert abs(tot[0] - tot[1]) <= 300
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from fluorosequencingimageanalysis_b200 import sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+lo, hi = sharding.field_block(5, 2, rank)
+local = {{"field": np.arange(lo, hi, dtype=np.int64), "fit": np.full((hi - lo, 3), float(rank))}}
+out = sharding.gather_packed(local)
+assert out["field"].tolist() == [0, 1, 2, 3, 4], out["field"]
+assert out["fit"].shape == (5, 3) and out["fit"][:3].max() == 0.0 and out["fit"][3:].min() == 1.0
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    """The N>1 path on CPU: two processes, gloo, each owns a contiguous field block, results are
+    concatenated on the host in rank order; there is no data-path collective."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
