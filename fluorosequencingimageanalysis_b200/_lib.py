@@ -26,7 +26,7 @@ class LmOpts(_c.Structure):
     """struct fsq_lm_opts (mpfit keyword defaults, agpy/mpfit/mpfit.py:600-605)."""
     _fields_ = [("ftol", _c.c_double), ("xtol", _c.c_double), ("gtol", _c.c_double),
                 ("factor", _c.c_double), ("maxiter", _c.c_int32), ("faithful", _c.c_int32),
-                ("want_perror", _c.c_int32), ("reserved", _c.c_int32)]
+                ("want_perror", _c.c_int32), ("solver", _c.c_int32)]
 
 
 class FsqError(RuntimeError):
@@ -99,11 +99,17 @@ def check(rc):
     raise FsqError("libfsq error %d: %s" % (rc, msg))
 
 
-def default_opts(faithful=True, want_perror=False, **kw):
+SOLVERS = {"minpack": 0, "fast64": 1, "fast": 2, "fast_mixed": 2, "fast32": 3}
+
+
+def default_opts(faithful=True, want_perror=False, solver="minpack", **kw):
     o = LmOpts()
     load().fsq_lm_default_opts(_c.byref(o))
     o.faithful = 1 if faithful else 0
     o.want_perror = 1 if want_perror else 0
+    if solver not in SOLVERS:
+        raise ValueError("solver must be one of %s" % sorted(SOLVERS))
+    o.solver = SOLVERS[solver]
     for k, v in kw.items():
         if v is not None:
             setattr(o, k, v)

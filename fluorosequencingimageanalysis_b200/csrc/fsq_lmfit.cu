@@ -962,12 +962,24 @@ static int launch_lm(const LmArgs& a, int G, bool pflib, cudaStream_t st) {
 
 }  // namespace fsq
 
+namespace fsq {
+// fsq_lmfast.cu
+int fast_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
+                        const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
+                        double* out_fit, int32_t* out_int, double* fit_img, unsigned long long* work_counter,
+                        cudaStream_t st);
+int fast_gaussfit_batch(const void* windows, int dtype_code, long long n, const double* p0, const double* lo,
+                        const double* hi, const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
+                        double* params, int32_t* status, int32_t* niter, int32_t* nfev, double* chi2,
+                        int32_t* n_damped, double* fit_img, unsigned long long* work_counter, cudaStream_t st);
+}  // namespace fsq
+
 using namespace fsq;
 
 extern "C" void fsq_lm_default_opts(fsq_lm_opts* o) {
     if (!o) return;
     o->ftol = 1e-10; o->xtol = 1e-10; o->gtol = 1e-10; o->factor = 100.0; o->maxiter = 200;   // mpfit.py:600-605
-    o->faithful = 1; o->want_perror = 0; o->reserved = 0;
+    o->faithful = 1; o->want_perror = 0; o->solver = FSQ_SOLVER_MINPACK;
 }
 
 static int check_opts(const fsq_lm_opts* o, const char* who) {
@@ -975,6 +987,10 @@ static int check_opts(const fsq_lm_opts* o, const char* who) {
     // mpfit.py:986-989 "input keywords are inconsistent"
     if (!(o->ftol > 0) || !(o->xtol > 0) || !(o->gtol > 0) || o->maxiter < 0 || !(o->factor > 0)) {
         set_error("%s: input keywords are inconsistent (ftol/xtol/gtol/factor must be > 0, maxiter >= 0)", who);
+        return FSQ_E_ARG;
+    }
+    if (o->solver < FSQ_SOLVER_MINPACK || o->solver > FSQ_SOLVER_FAST32) {
+        set_error("%s: unknown solver %d", who, o->solver);
         return FSQ_E_ARG;
     }
     return FSQ_OK;
@@ -1004,6 +1020,12 @@ extern "C" int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n
         return FSQ_E_ARG;
     }
     if (opts->want_perror && !perror) { set_error("fsq_gaussfit_batch: want_perror set but perror is NULL"); return FSQ_E_ARG; }
+    if (opts->solver != FSQ_SOLVER_MINPACK) {
+        if (win != 5) { set_error("fsq_gaussfit_batch: the FAST solvers take 5x5 windows (got %d); use FSQ_SOLVER_MINPACK", win); return FSQ_E_ARG; }
+        if (opts->want_perror) { set_error("fsq_gaussfit_batch: want_perror needs FSQ_SOLVER_MINPACK"); return FSQ_E_ARG; }
+        return fast_gaussfit_batch(windows, dtype_code, n, p0, lo, hi, lim_lo, lim_hi, opts, params, status, niter, nfev,
+                                   chi2, n_qrsolv, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);
+    }
     LmArgs a;
     memset(&a, 0, sizeof(a));
     a.windows = windows; a.wdtype = dtype_code; a.win = win;
@@ -1058,6 +1080,9 @@ extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_fram
         set_error("fsq_fit_candidates: unsupported frame dtype code %d", dtype_code);
         return FSQ_E_ARG;
     }
+    if (opts->solver != FSQ_SOLVER_MINPACK)
+        return fast_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
+                                   out_int, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);
     LmArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = frames; a.fdtype = dtype_code; a.H = H; a.W = W;

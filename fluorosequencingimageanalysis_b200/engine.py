@@ -152,14 +152,14 @@ def detect_cm32(det):
 
 
 def fit_candidates(frames, cand_hw, cand_frame, n, faithful=True, want_fit_img=False, n_dev=None,
-                   opts=None):
+                   opts=None, solver="minpack"):
     """pflib.find_peptides' per-candidate loop (pflib.py:441-477) for n candidates.
     Returns (out_fit [n,12] f64, out_int [n,4] i32, fit_img [n,25] f64 | None) on the device."""
     L = _lib.load()
     frames = to_device_frames(frames)
     F, H, W = frames.shape
     dev = frames.device
-    o = opts or _lib.default_opts(faithful=faithful)
+    o = opts or _lib.default_opts(faithful=faithful, solver=solver)
     out_fit = torch.empty((n, 12), dtype=torch.float64, device=dev)
     out_int = torch.empty((n, 4), dtype=torch.int32, device=dev)
     fit_img = torch.empty((n, 25), dtype=torch.float64, device=dev) if want_fit_img else None
@@ -178,7 +178,7 @@ class FitBatch(object):
 
 
 def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perror=False,
-                   want_fit_img=False, opts=None, **mpfit_kw):
+                   want_fit_img=False, opts=None, solver="minpack", **mpfit_kw):
     """gaussfitter.gaussfit -> mpfit (agpy/gaussfitter.py:142-255) for n windows [n,win,win]."""
     L = _lib.load()
     require_cuda()
@@ -208,7 +208,7 @@ def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perr
     hi = dv(hi, torch.float64).reshape(n, 7)
     lim_lo = dv(lim_lo, torch.uint8).reshape(n, 7)
     lim_hi = dv(lim_hi, torch.uint8).reshape(n, 7)
-    o = opts or _lib.default_opts(faithful=faithful, want_perror=want_perror, **mpfit_kw)
+    o = opts or _lib.default_opts(faithful=faithful, want_perror=want_perror, solver=solver, **mpfit_kw)
     r = FitBatch()
     r.params = torch.empty((n, 7), dtype=torch.float64, device=dev)
     r.perror = torch.empty((n, 7), dtype=torch.float64, device=dev) if want_perror else None
@@ -297,14 +297,14 @@ class FieldResults(object):
 
 
 def find_peptides_batch(frames, median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX,
-                        c_std=2, faithful=True, want_fit_img=False, to_host=True):
+                        c_std=2, faithful=True, want_fit_img=False, to_host=True, solver="minpack"):
     """Detection + per-candidate fit + metrics for a batch of frames (the GPU-relevant part of
     pflib.find_peptides, pflib.py:434-477).  The R^2 gate / consolidation / re-key
     (pflib.py:466-468, 479-519) operate on these packed arrays -- see pflib.consolidate_packed."""
     frames = to_device_frames(frames)
     det = detect_batch(frames, median_filter_size, correlation_matrix, c_std)
     fit, ints, fit_img = fit_candidates(frames, det.cand_hw, det.cand_frame, det.total,
-                                        faithful=faithful, want_fit_img=want_fit_img)
+                                        faithful=faithful, want_fit_img=want_fit_img, solver=solver)
     r = FieldResults()
     r.shape = tuple(frames.shape)
     if to_host:
@@ -329,7 +329,7 @@ class FieldPipeline(object):
 
     def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
                  median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
-                 device=None):
+                 device=None, solver="minpack"):
         require_cuda()
         self.L = _lib.load()
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -341,7 +341,8 @@ class FieldPipeline(object):
         self.K = _check_kernel(correlation_matrix)
         self.mf = int(median_filter_size)
         self.c_std = float(c_std)
-        self.opts = _lib.default_opts(faithful=faithful)
+        self.opts = _lib.default_opts(faithful=faithful, solver=solver)
+        self.solver = solver
         if cap_per_frame is None:
             cap_per_frame = max(1024, int(0.06 * H * W))
         self.cap = int(cap_per_frame) * self.F
@@ -355,7 +356,8 @@ class FieldPipeline(object):
         self.out_fit = torch.empty((self.cap, 12), dtype=torch.float64, device=d)
         self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
         self.counter = torch.zeros(1, dtype=torch.int64, device=d)
-        self.kernels_per_run = 7          # cm, thr, rowmask, rowscan, framescan, emit, lmfit
+        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (2 for the mixed solver)
+        self.kernels_per_run = 6 + (2 if _lib.SOLVERS[solver] == 2 else 1)
 
     def run(self, frames_dev, fit=True):
         """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype)."""

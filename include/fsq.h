@@ -94,9 +94,26 @@ typedef struct fsq_lm_opts {
     int32_t maxiter;    /* 200   */
     int32_t faithful;   /* 1: reproduce the reference's qrsolv diagonal-view behaviour
                               (mpfit.py:1915,1956,1976-1977); 0: clean MINPACK            */
-    int32_t want_perror;/* 1: compute covariance -> perror (mpfit.py:1361-1388)           */
-    int32_t reserved;
+    int32_t want_perror;/* 1: compute covariance -> perror (mpfit.py:1361-1388); MINPACK solver only */
+    int32_t solver;     /* FSQ_SOLVER_*                                                    */
 } fsq_lm_opts;
+
+/* Solvers behind the two fit entry points.
+ *  MINPACK     the reference's algorithm operation for operation in FP64: forward-difference
+ *              Jacobian (8 model evaluations per iteration), pivoted Householder QR, lmpar/qrsolv
+ *              (with the reference's diagonal-view behaviour when faithful = 1).  One sub-warp per
+ *              window.  This is the parity instrument.
+ *  FAST64      the same bounded trust-region LM (same pegging / alpha / snapping / termination
+ *              rules) driven by the analytic Jacobian through column-scaled normal equations and
+ *              a register-resident Cholesky; one thread per window, FP64.  5x5 windows.
+ *  FAST_MIXED  FAST in FP32 with loosened tolerances, then FAST64 from its end point.
+ *  FAST32      the FP32 phase alone (parameters good to ~1e-3 relative).
+ * `faithful` and `want_perror` are ignored by the FAST solvers; n_qrsolv then counts damped
+ * (par > 0) solves, so n_qrsolv == 0 still means "every step was a plain Gauss-Newton step". */
+#define FSQ_SOLVER_MINPACK    0
+#define FSQ_SOLVER_FAST64     1
+#define FSQ_SOLVER_FAST_MIXED 2
+#define FSQ_SOLVER_FAST32     3
 
 void fsq_lm_default_opts(fsq_lm_opts* o);
 

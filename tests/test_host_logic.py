@@ -18,8 +18,8 @@ from oracle import pflib_oracle as po
 def test_median25_network_is_a_median():
     """A comparator network selects rank 12 of 25 for ALL inputs iff it does for all 2^25
     0/1 inputs.  The network is parsed from the CUDA source, so the test checks what ships."""
-    src = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_detect.cu")).read()
-    body = src[src.index("__device__ __forceinline__ int median25"):src.index("#undef FSQ_CE")]
+    src = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_median.cuh")).read()
+    body = src[src.index("median25(V* p)"):src.index("#undef FSQ_CE")]
     ces = [(int(a), int(b)) for a, b in re.findall(r"FSQ_CE\((\d+),\s*(\d+)\)", body)]
     assert len(ces) == 99
     assert "return p[12]" in body

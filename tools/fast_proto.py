@@ -96,13 +96,14 @@ def tri_solve(L, okc, rhs):
     return y
 
 
-def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, maxiter=200,
+def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fdt=None, maxiter=200,
              ftol=1e-10, xtol=1e-10, gtol=1e-10, factor=100.0, rank_eps=None, verbose=False):
     """data [N,win,win]; returns dict(params, status, niter, nfev, chi2)."""
     N, win, _ = data.shape
     P = win * win
     rr, cc = [a.ravel() for a in np.indices((win, win))]
-    d = data.reshape(N, P).astype(dt)
+    fdt = fdt or dt                                        # dtype of model / residual / chi^2
+    d = data.reshape(N, P).astype(fdt)
     x = p0.astype(np.float64).copy()
     lo, hi = lo.astype(np.float64), hi.astype(np.float64)
     ql, qu = lim_lo.astype(bool), lim_hi.astype(bool)
@@ -118,9 +119,10 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, ma
     xnorm = np.zeros(N)
     diag = np.ones((N, 7))
     need = np.ones(N, dtype=bool)
-    m0 = model_only(x, rr, cc, dt)
+    m0 = model_only(x, rr, cc, fdt)
     f = d - m0
-    fnorm = np.sqrt((f.astype(acc) ** 2).sum(axis=1)).astype(np.float64)
+    facc = np.float64 if fdt == np.float64 else acc
+    fnorm = np.sqrt((f.astype(facc) ** 2).sum(axis=1)).astype(np.float64)
     fnorm1 = np.full(N, -1.0)
     A = np.zeros((N, 7, 7))
     g = np.zeros((N, 7))
@@ -136,7 +138,7 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, ma
         if len(idx):
             E, J = model_jac(x[idx], rr, cc, dt)
             J = -J                                         # d(residual)/dp
-            fi = f[idx]
+            fi = f[idx].astype(dt)
             gi = np.einsum("npk,np->nk", J.astype(acc), fi.astype(acc)).astype(np.float64)
             lp = ql[idx] & (x[idx] == lo[idx])
             up = qu[idx] & (x[idx] == hi[idx])
@@ -238,13 +240,13 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, ma
         xnew = np.where(ql[idx] & (xnew <= llim1), lo[idx], xnew)
         pnorm = np.sqrt(((Di * p) ** 2).sum(axis=1))
         dl = np.where(niter[idx] == 1, np.minimum(dl, pnorm), dl)
-        f1 = d[idx] - model_only(xnew, rr, cc, dt)
-        fn1 = np.sqrt((f1.astype(acc) ** 2).sum(axis=1)).astype(np.float64)
+        f1 = d[idx] - model_only(xnew, rr, cc, fdt)
+        fn1 = np.sqrt((f1.astype(facc) ** 2).sum(axis=1)).astype(np.float64)
         nfev[idx] += 1
         fn = fnorm[idx]
         actred = np.where(0.1 * fn1 < fn, 1.0 - (fn1 / fn) ** 2, -1.0)
         pAp = np.einsum("nk,nkl,nl->n", p, Ai, p)          # |J p|^2 (p already scaled by alpha)
-        t1sq = np.maximum(pAp, 0) / fn ** 2
+        t1sq = alpha ** 2 * np.maximum(pAp, 0) / fn ** 2   # mpfit applies alpha once more here (:1265)
         t2sq = alpha * pr * pnorm ** 2 / fn ** 2
         prered = t1sq + 2 * t2sq
         dirder = -(t1sq + t2sq)
@@ -284,6 +286,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--acc", default="f64")
+    ap.add_argument("--fdt", default="")
     ap.add_argument("--ftol", type=float, default=1e-10)
     ap.add_argument("--xtol", type=float, default=1e-10)
     ap.add_argument("--n", type=int, default=0)
@@ -301,7 +304,8 @@ def main():
     dt = {"f32": np.float32, "f64": np.float64}[a.dtype]
     acc = {"f32": np.float32, "f64": np.float64}[a.acc]
     t = time.time()
-    r = fast_fit(subs, p0, lo, hi, ll, lh, dt=dt, acc=acc, ftol=a.ftol, xtol=a.xtol)
+    fdt = {"f32": np.float32, "f64": np.float64, "": None}[a.fdt]
+    r = fast_fit(subs, p0, lo, hi, ll, lh, dt=dt, acc=acc, fdt=fdt, ftol=a.ftol, xtol=a.xtol)
     print("time %.1fs" % (time.time() - t))
     P = r["params"]
     for key in ("clean", "ref"):
