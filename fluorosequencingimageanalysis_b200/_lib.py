@@ -99,7 +99,7 @@ def check(rc):
     raise FsqError("libfsq error %d: %s" % (rc, msg))
 
 
-SOLVERS = {"minpack": 0, "fast64": 1, "fast": 2, "fast_mixed": 2, "fast32": 3}
+SOLVERS = {"minpack": 0, "fast64": 1, "fast": 2}
 
 
 def default_opts(faithful=True, want_perror=False, solver="minpack", **kw):

@@ -12,10 +12,7 @@
 // divergence between the lanes of a warp inside an iteration; a lane whose fit has ended pulls
 // the next window from an atomic work queue (persistent grid), so long fits never hold a warp.
 //
-// Precision (template T): T = double is the parity flavour; T = float is a coarse first phase
-// (pixel math, accumulators and the Cholesky in FP32, parameters and trust-region bookkeeping
-// in FP64) whose end point a T = double launch then polishes to the reference's 1e-10
-// tolerances (opts.solver = FSQ_SOLVER_FAST_MIXED).
+// All arithmetic in FP64 (the T = float instantiation of the pixel math is not built).
 //
 // What is NOT reproduced on purpose: the rounding noise of the reference's finite-difference
 // rotation column at the pflib start point and the qrsolv diagonal-view behaviour -- those are
@@ -588,21 +585,10 @@ static int launch_one(const FastArgs& a, cudaStream_t st) {
     return FSQ_OK;
 }
 
-// solver: FSQ_SOLVER_FAST64 (one FP64 launch), FSQ_SOLVER_FAST_MIXED (FP32 coarse launch with loosened
-// tolerances, then an FP64 polish launch from its end point), FSQ_SOLVER_FAST32 (FP32 launch only).
+// FSQ_SOLVER_FAST64: one FP64 launch.
 template <bool PFLIB>
 int launch_fast(FastArgs a, cudaStream_t st) {
-    const int solver = a.o.solver;
-    if (solver == FSQ_SOLVER_FAST64) {
-        a.resume = 0; a.write_metrics = 1;
-        return launch_one<double, PFLIB>(a, st);
-    }
-    FastArgs c = a;
-    c.o.ftol = fmax(a.o.ftol, 1e-5); c.o.xtol = fmax(a.o.xtol, 1e-7); c.o.gtol = fmax(a.o.gtol, 1e-7);
-    c.resume = 0; c.write_metrics = (solver == FSQ_SOLVER_FAST32) ? 1 : 0;
-    int rc = launch_one<float, PFLIB>(c, st);
-    if (rc != FSQ_OK || solver == FSQ_SOLVER_FAST32) return rc;
-    a.resume = 1; a.write_metrics = 1;
+    a.resume = 0; a.write_metrics = 1;
     return launch_one<double, PFLIB>(a, st);
 }
 

@@ -963,6 +963,11 @@ static int launch_lm(const LmArgs& a, int G, bool pflib, cudaStream_t st) {
 }  // namespace fsq
 
 namespace fsq {
+// fsq_lmwarp.cu
+int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
+                        const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
+                        double* out_fit, int32_t* out_int, double* fit_img, unsigned long long* work_counter,
+                        cudaStream_t st);
 // fsq_lmfast.cu
 int fast_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
@@ -989,7 +994,7 @@ static int check_opts(const fsq_lm_opts* o, const char* who) {
         set_error("%s: input keywords are inconsistent (ftol/xtol/gtol/factor must be > 0, maxiter >= 0)", who);
         return FSQ_E_ARG;
     }
-    if (o->solver < FSQ_SOLVER_MINPACK || o->solver > FSQ_SOLVER_FAST32) {
+    if (o->solver < FSQ_SOLVER_MINPACK || o->solver > FSQ_SOLVER_FAST) {
         set_error("%s: unknown solver %d", who, o->solver);
         return FSQ_E_ARG;
     }
@@ -1080,6 +1085,9 @@ extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_fram
         set_error("fsq_fit_candidates: unsupported frame dtype code %d", dtype_code);
         return FSQ_E_ARG;
     }
+    if (opts->solver == FSQ_SOLVER_FAST)
+        return warp_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
+                                   out_int, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);
     if (opts->solver != FSQ_SOLVER_MINPACK)
         return fast_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
                                    out_int, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);

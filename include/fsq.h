@@ -103,17 +103,19 @@ typedef struct fsq_lm_opts {
  *              Jacobian (8 model evaluations per iteration), pivoted Householder QR, lmpar/qrsolv
  *              (with the reference's diagonal-view behaviour when faithful = 1).  One sub-warp per
  *              window.  This is the parity instrument.
- *  FAST64      the same bounded trust-region LM (same pegging / alpha / snapping / termination
- *              rules) driven by the analytic Jacobian through column-scaled normal equations and
- *              a register-resident Cholesky; one thread per window, FP64.  5x5 windows.
- *  FAST_MIXED  FAST in FP32 with loosened tolerances, then FAST64 from its end point.
- *  FAST32      the FP32 phase alone (parameters good to ~1e-3 relative).
+ *  FAST        the production fitter of the frame path (fsq_fit_candidates): the same bounded
+ *              trust-region LM (same pegging / alpha / snapping / termination rules) driven by the
+ *              analytic Jacobian through column-scaled normal equations and a 7x7 Cholesky.  One
+ *              thread per 5x5 window, the 32 fits of a warp in lock step, one pass over the
+ *              window per LM iteration; residual / chi^2 in FP64, Jacobian and normal equations
+ *              in FP32.  (fsq_gaussfit_batch runs FAST64 for this code.)
+ *  FAST64      the same algorithm entirely in FP64, one thread per window, two passes per
+ *              iteration; 5x5 windows.  Cross-check of FAST and generic-window entry point.
  * `faithful` and `want_perror` are ignored by the FAST solvers; n_qrsolv then counts damped
  * (par > 0) solves, so n_qrsolv == 0 still means "every step was a plain Gauss-Newton step". */
 #define FSQ_SOLVER_MINPACK    0
 #define FSQ_SOLVER_FAST64     1
-#define FSQ_SOLVER_FAST_MIXED 2
-#define FSQ_SOLVER_FAST32     3
+#define FSQ_SOLVER_FAST       2
 
 void fsq_lm_default_opts(fsq_lm_opts* o);
 

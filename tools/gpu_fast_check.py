@@ -10,7 +10,7 @@ G = os.path.join(ROOT, "tests", "golden")
 g = np.load(os.path.join(G, "fits5_seed0.npz")); st = np.load(os.path.join(G, "stable5_seed0.npz"))
 img = synth.synth_frame(0)
 out = {}
-for solver in ("minpack", "fast64", "fast", "fast32"):
+for solver in ("minpack", "fast64", "fast"):
     for faithful in ((True, False) if solver == "minpack" else (False,)):
         res = engine.find_peptides_batch(img, faithful=faithful, want_fit_img=True, solver=solver)
         P = res.fit[:, [2, 3, 0, 1, 4, 5, 6]].copy()
@@ -30,12 +30,12 @@ for solver in ("minpack", "fast64", "fast", "fast32"):
             dict(zip(*[x.tolist() for x in np.unique(res.ints[:, 0], return_counts=True)])))
         print(line, flush=True)
 # fast64 vs fast (mixed) vs numpy prototype
-for a_, b_ in (("fast64", "fast"), ("fast64", "minpack"), ("fast64", "fast32")):
+for a_, b_ in (("fast64", "fast"), ("fast64", "minpack")):
     A, B = out[a_][0], out[b_][0]
     m = (np.abs(A[:, :6] - B[:, :6]) / np.maximum(np.abs(A[:, :6]), 1e-300)).max(axis=1)
     print("%s vs %s: max-rel-diff pct 50/90/99 %s frac<1e-4 %.4f <1e-6 %.4f" % (a_, b_, np.percentile(m, [50, 90, 99]), np.mean(m < 1e-4), np.mean(m < 1e-6)))
-print("metrics fast64 vs minpack-clean where params agree:",)
-A, B = out["fast64"], out["minpack"]
+print("metrics fast vs minpack-clean where params agree:",)
+A, B = out["fast"], out["minpack"]
 same = agree(A[0], B[0], tol=1e-8, ctol=1e-8)
 print("  n same %d  r2 maxdiff %.3g rmse maxrel %.3g s_n maxrel %.3g" % (same.sum(), np.abs(A[1][same, 8] - B[1][same, 8]).max(),
       (np.abs(A[1][same, 7] - B[1][same, 7]) / B[1][same, 7]).max(), (np.abs(A[1][:, 9] - B[1][:, 9]) / np.abs(B[1][:, 9])).max()))
@@ -46,7 +46,7 @@ fr = synth.synth_timetrace(1, n_frames=40)
 frd = engine.to_device_frames(fr)
 det = engine.detect_batch(frd)
 print("candidates", det.total)
-for solver, faithful in (("minpack", True), ("minpack", False), ("fast64", False), ("fast", False), ("fast32", False)):
+for solver, faithful in (("minpack", False), ("fast64", False), ("fast", False)):
     ts = []
     for rep in range(4):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
