@@ -114,17 +114,72 @@ fit_prep_kernel(const WarpArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------
-// 7x7 Cholesky of the column-scaled, damped normal matrix
-//     M = S^-1 A S^-1 + par (D/S)^2        (unit diagonal at par = 0)
-// A read from shared memory ([entry][thread]); singular pivots are skipped (Li = 0).
+// Branch-free FP64 helpers of the pass.  exp: Cody-Waite reduction by ln2 + degree-12 Taylor
+// polynomial (|r| <= ln2/2: 2 ulp, measured against numpy.exp), argument <= 0 and bounded by the
+// pflib limits (widths >= 0.75, centres in [2,3] => |arg| < 64), so no range checks.
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const float (&iS)[WNP], const float (&diag)[WNP],
+__device__ __forceinline__ double w_exp_neg(double u) {
+    const double kf = fma(u, 1.4426950408889634, 6755399441055744.0);        // round(u / ln2) in the low word
+    const int k = __double2loint(kf);
+    const double kd = kf - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, u);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;                                   // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// sin / cos of an angle given in DEGREES (gaussfitter.py:115 converts with pi/180), exact at
+// multiples of 90: reduce by quarter turns in degrees (exact), then odd / even polynomials on
+// |r| <= pi/4.
+__device__ __forceinline__ void w_sincos_deg(double th, double* sn, double* cs) {
+    const double qf = rint(th * (1.0 / 90.0));
+    const int q = (int)qf;
+    const double r = fma(qf, -90.0, th) * WQ_DEG2RAD;
+    const double r2 = r * r;
+    double ps = 1.58969099521155010221e-10;          // 1/13!
+    ps = fma(ps, r2, -2.50521083854417187751e-08);
+    ps = fma(ps, r2, 2.75573192239858906526e-06);
+    ps = fma(ps, r2, -1.98412698412698412698e-04);
+    ps = fma(ps, r2, 8.33333333333333333333e-03);
+    ps = fma(ps, r2, -1.66666666666666666667e-01);
+    const double s = fma(ps * r2, r, r);
+    double pc = -1.14707455977297247139e-11;         // -1/14!
+    pc = fma(pc, r2, 2.08767569878680989792e-09);
+    pc = fma(pc, r2, -2.75573192239858906526e-07);
+    pc = fma(pc, r2, 2.48015873015873015873e-05);
+    pc = fma(pc, r2, -1.38888888888888888889e-03);
+    pc = fma(pc, r2, 4.16666666666666666667e-02);
+    pc = fma(pc, r2, -0.5);
+    const double c = fma(pc, r2, 1.0);
+    const bool swap = q & 1;
+    const double ss = swap ? c : s, cc = swap ? s : c;
+    *sn = (q & 2) ? -ss : ss;
+    *cs = ((q + 1) & 2) ? -cc : cc;
+}
+
+// -------------------------------------------------------------------------------------------
+// 7x7 Cholesky of the column-scaled, damped normal matrix
+//     M = As + par * T,   As = S^-1 A S^-1 (unit diagonal),  T = (D/S)^2
+// As read from shared memory ([entry][thread]); singular pivots are skipped (Li = 0).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const float (&T)[WNP],
                                             float par, float (&L)[WNT], float (&Li)[WNP], float eps) {
     unsigned ok = 0;
 #pragma unroll
     for (int j = 0; j < WNP; ++j) {
-        const float dsj = diag[j] * iS[j];
-        float dj = fmaf(par * dsj, dsj, sA[wtri(j, j) * WTHREADS] * (iS[j] * iS[j]));
+        float dj = fmaf(par, T[j], sA[wtri(j, j) * WTHREADS]);
 #pragma unroll
         for (int k = 0; k < j; ++k) dj = fmaf(-L[wtri(j, k)], L[wtri(j, k)], dj);
         const bool good = dj > eps;
@@ -134,7 +189,7 @@ __device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const 
         ok |= (good ? 1u : 0u) << j;
 #pragma unroll
         for (int i = j + 1; i < WNP; ++i) {
-            float sacc = sA[wtri(i, j) * WTHREADS] * (iS[i] * iS[j]);
+            float sacc = sA[wtri(i, j) * WTHREADS];
 #pragma unroll
             for (int k = 0; k < j; ++k) sacc = fmaf(-L[wtri(i, k)], L[wtri(j, k)], sacc);
             L[wtri(i, j)] = sacc * inv;
@@ -168,7 +223,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
                                        float (&A)[WNT], float (&g)[WNP], double& ss_out) {
     const double Hh = pt[0], Aa = pt[1];
     double sn, cs;
-    sincos(WQ_DEG2RAD * pt[6], &sn, &cs);                                     // gaussfitter.py:115
+    w_sincos_deg(pt[6], &sn, &cs);                                            // gaussfitter.py:115
     const double iwx = 1.0 / pt[4], iwy = 1.0 / pt[5];
     const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
     double ca[5], cb[5];
@@ -187,16 +242,17 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
 #pragma unroll
     for (int i = 0; i < WNP; ++i) g[i] = 0.0f;
     double ss = 0.0;
+    double dx = pt[3];                                  // x = row index pairs with p[3]
 #pragma unroll 1
     for (int r = 0; r < 5; ++r) {
-        const double dx = pt[3] - (double)r;            // x = row index pairs with p[3]
         const double ra = dx * cxs, rb = dx * sys;
         const float raf = (float)ra, rbf = (float)rb;
         const double* drow = sd + r * 5 * WTHREADS;
+        dx -= 1.0;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             const double av = ra - ca[c], bv = rb + cb[c];
-            const double E = exp(-0.5 * fma(bv, bv, av * av));
+            const double E = w_exp_neg(-0.5 * fma(bv, bv, av * av));
             const double f = drow[c * WTHREADS] - fma(Aa, E, Hh);
             ss = fma(f, f, ss);
             const float af = raf - caf[c], bf = rbf + cbf[c];
@@ -205,7 +261,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
             const float AEa = AE * af, AEb = AE * bf;
             float j[WNP];
             j[1] = -Ef;
-            j[2] = -(AEa * sx - AEb * cyw);             // d/d p[2] (centre along axis 1)
+            j[2] = AEb * cyw - AEa * sx;                // d/d p[2] (centre along axis 1)
             j[3] = AEa * cxw + AEb * sy;                // d/d p[3] (centre along axis 0)
             j[4] = -AEa * af * iwxf;
             j[5] = -AEb * bf * iwyf;
@@ -226,19 +282,21 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
 }
 
 enum { MODE_FIRST = 0, MODE_TRIAL = 1 };
+#define WQ_TINYF 1.0e-37f
 
 __global__ void __launch_bounds__(WTHREADS, 3)
 lmwarp_kernel(const WarpArgs a) {
     __shared__ double s_d[25 * WTHREADS];
-    __shared__ float s_A[WNT * WTHREADS];
-    __shared__ float s_g[WNP * WTHREADS];
+    __shared__ float s_A[WNT * WTHREADS];      // column-scaled J^T J at the current point
+    __shared__ float s_g[WNP * WTHREADS];      // column-scaled J^T f
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     double* const sd = s_d + tid;
     float* const sA = s_A + tid;
     float* const sg = s_g + tid;
 
-    const double ftol = a.o.ftol, xtol = a.o.xtol, gtol = a.o.gtol, factor = a.o.factor;
+    const float ftol = (float)a.o.ftol, xtol = (float)a.o.xtol, gtol = (float)a.o.gtol, factor = (float)a.o.factor;
+    const float machep = (float)WQ_MACHEP;
     const int maxiter = a.o.maxiter;
     long long n_total = a.n;
     if (a.n_dev) { const long long nd = *a.n_dev; n_total = nd < a.n ? nd : a.n; }
@@ -251,8 +309,8 @@ lmwarp_kernel(const WarpArgs a) {
     unsigned lpeg = 0, upeg = 0;
     bool nonfinite = false;
     double x[WNP], y[WNP];
-    double lo1 = 0.0, fnorm = -1.0, fnorm1 = -1.0, delta = 0.0, par = 0.0, xnorm = 0.0, gnorm = 0.0;
-    double pnorm = 0.0, prered = 0.0, dirder = 0.0;
+    double lo1 = 0.0, ss0 = -1.0, ss1 = -1.0;           // chi^2 at x, chi^2 of the last trial point
+    float delta = 0.0f, par = 0.0f, xnorm = 0.0f, gnorm = 0.0f, pnorm = 0.0f, prered = 0.0f, dirder = 0.0f, rss0 = 0.0f;
     float diag[WNP], iS[WNP];
 #pragma unroll
     for (int j = 0; j < WNP; ++j) { x[j] = 0.0; y[j] = 1.0; diag[j] = 1.0f; iS[j] = 1.0f; }
@@ -272,7 +330,7 @@ lmwarp_kernel(const WarpArgs a) {
                 else {
                     cand_h = a.cand_hw[2 * idx]; cand_w = a.cand_hw[2 * idx + 1];
                     const size_t fbase = (size_t)a.cand_frame[idx] * a.H * a.W + (size_t)(cand_h - 2) * a.W + (cand_w - 2);
-#pragma unroll
+#pragma unroll 1
                     for (int r = 0; r < 5; ++r)
 #pragma unroll
                         for (int c = 0; c < 5; ++c)
@@ -288,7 +346,7 @@ lmwarp_kernel(const WarpArgs a) {
                         y[j] = x[j];
                     }
                     active = true; mode = MODE_FIRST; status = 0; niter = 1; nfev = 0; n_damped = 0;
-                    fnorm = -1.0; fnorm1 = -1.0; par = 0.0; nonfinite = false;
+                    ss0 = -1.0; ss1 = -1.0; par = 0.0f; nonfinite = false;
                 }
             }
         }
@@ -303,44 +361,44 @@ lmwarp_kernel(const WarpArgs a) {
 
             bool have_new = false;
             if (mode == MODE_FIRST) {
-                fnorm = sqrt(ss);                                                        // mpfit.py:999, :1019
+                ss0 = ss;                                                                // mpfit.py:999, :1019
                 have_new = true;
             } else {
                 // ---------------------------------------------------------- trial bookkeeping (:1245-1335)
-                fnorm1 = sqrt(ss);
-                double actred = -1.0;
-                if (0.1 * fnorm1 < fnorm) { const double r = fnorm1 / fnorm; actred = 1.0 - r * r; }
-                double ratio = 0.0;
-                if (prered != 0.0) ratio = actred / prered;
-                if (ratio <= 0.25) {                                                     // :1276-1288
-                    double temp;
-                    if (actred >= 0.0) temp = 0.5;
-                    else temp = 0.5 * dirder / (dirder + 0.5 * actred);
-                    if ((0.1 * fnorm1 >= fnorm) || (temp < 0.1)) temp = 0.1;
-                    delta = temp * fmin(delta, pnorm / 0.1);
-                    par = par / temp;
-                } else if ((par == 0.0) || (ratio >= 0.75)) {
-                    delta = pnorm / 0.5;
-                    par = 0.5 * par;
+                ss1 = ss;
+                float actred = -1.0f;
+                if (0.01 * ss1 < ss0) actred = (float)(ss0 - ss1) * rss0;               // 1 - (fnorm1/fnorm)^2
+                float ratio = 0.0f;
+                if (prered != 0.0f) ratio = __fdividef(actred, prered);
+                if (ratio <= 0.25f) {                                                    // :1276-1288
+                    float temp;
+                    if (actred >= 0.0f) temp = 0.5f;
+                    else temp = __fdividef(0.5f * dirder, dirder + 0.5f * actred);
+                    if ((0.01 * ss1 >= ss0) || (temp < 0.1f)) temp = 0.1f;
+                    delta = temp * fminf(delta, pnorm * 10.0f);
+                    par = __fdividef(par, temp);
+                } else if ((par == 0.0f) || (ratio >= 0.75f)) {
+                    delta = pnorm * 2.0f;
+                    par = 0.5f * par;
                 }
-                const bool accepted = ratio >= 0.0001;                                   // :1291-1298
+                const bool accepted = ratio >= 0.0001f;                                  // :1291-1298
                 if (accepted) {
-                    double s = 0.0;
+                    float s = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < WNP; ++j) { x[j] = y[j]; const double t = (double)diag[j] * x[j]; s += t * t; }
-                    xnorm = sqrt(s);
-                    fnorm = fnorm1;
+                    for (int j = 0; j < WNP; ++j) { x[j] = y[j]; const float t = diag[j] * (float)x[j]; s = fmaf(t, t, s); }
+                    xnorm = sqrtf(s);
+                    ss0 = ss1;
                     ++niter;
                 }
-                const bool c1 = (fabs(actred) <= ftol) && (prered <= ftol) && (0.5 * ratio <= 1.0);   // :1301-1323
+                const bool c1 = (fabsf(actred) <= ftol) && (prered <= ftol) && (0.5f * ratio <= 1.0f);   // :1301-1323
                 if (c1) status = 1;
                 if (delta <= xtol * xnorm) status = 2;
                 if (c1 && status == 2) status = 3;
                 if (status == 0) {
                     if (niter >= maxiter) status = 5;
-                    if ((fabs(actred) <= WQ_MACHEP) && (prered <= WQ_MACHEP) && (0.5 * ratio <= 1.0)) status = 6;
-                    if (delta <= WQ_MACHEP * xnorm) status = 7;
-                    if (gnorm <= WQ_MACHEP) status = 8;
+                    if ((fabsf(actred) <= machep) && (prered <= machep) && (0.5f * ratio <= 1.0f)) status = 6;
+                    if (delta <= machep * xnorm) status = 7;
+                    if (gnorm <= machep) status = 8;
                 }
                 if (status == 0 && !accepted && (nonfinite || !isfinite(ratio))) status = -16;   // :1330-1335
                 have_new = accepted;
@@ -348,6 +406,7 @@ lmwarp_kernel(const WarpArgs a) {
 
             if (status == 0 && have_new) {
                 // ---------------------------------------------------------- new linearisation at x
+                rss0 = __fdividef(1.0f, (float)ss0);
                 // pegged parameters: zero the column when the gradient pushes outwards (:1073-1091)
                 lpeg = 0; upeg = 0;
 #pragma unroll
@@ -356,11 +415,10 @@ lmwarp_kernel(const WarpArgs a) {
                     const bool up = ((PF_QUL >> j) & 1u) && (x[j] == pf_hi(j));
                     lpeg |= (lp ? 1u : 0u) << j; upeg |= (up ? 1u : 0u) << j;
                     const bool zero = (lp && gn[j] > 0.0f) || (up && gn[j] < 0.0f);
-                    if (zero) {
-                        gn[j] = 0.0f;
+                    const float keep = zero ? 0.0f : 1.0f;
+                    gn[j] *= keep;
 #pragma unroll
-                        for (int k = 0; k < WNP; ++k) An[(k >= j) ? wtri(k, j) : wtri(j, k)] = 0.0f;
-                    }
+                    for (int k = 0; k < WNP; ++k) An[(k >= j) ? wtri(k, j) : wtri(j, k)] *= keep;
                 }
                 float acn[WNP];
                 float gmax = 0.0f;
@@ -370,126 +428,117 @@ lmwarp_kernel(const WarpArgs a) {
                     const float rs = ajj > 0.0f ? rsqrtf(ajj) : 0.0f;
                     acn[j] = ajj * rs;                                                   // column norms (:1758)
                     iS[j] = ajj > 0.0f ? rs : 1.0f;
-                    if (ajj > 0.0f) gmax = fmaxf(gmax, fabsf(gn[j] * rs));               // :1142-1148
+                    gn[j] *= iS[j];                                                      // scaled gradient
+                    if (ajj > 0.0f) gmax = fmaxf(gmax, fabsf(gn[j]));                    // :1142-1148
                 }
-                gnorm = (fnorm != 0.0) ? (double)gmax / fnorm : 0.0;
+                gnorm = (ss0 != 0.0) ? gmax * sqrtf(rss0) : 0.0f;
                 if (mode == MODE_FIRST) {                                                // :1099-1110
-                    double s = 0.0;
+                    float s = 0.0f;
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) {
                         diag[j] = (acn[j] == 0.0f) ? 1.0f : acn[j];
-                        const double t = (double)diag[j] * x[j];
-                        s += t * t;
+                        const float t = diag[j] * (float)x[j];
+                        s = fmaf(t, t, s);
                     }
-                    xnorm = sqrt(s);
+                    xnorm = sqrtf(s);
                     delta = factor * xnorm;
-                    if (delta == 0.0) delta = factor;
+                    if (delta == 0.0f) delta = factor;
                 }
                 if (gnorm <= gtol) status = 4;                                           // :1151
                 else if (maxiter == 0) status = 5;
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) diag[j] = fmaxf(diag[j], acn[j]);          // :1160
 #pragma unroll
-                for (int i = 0; i < WNT; ++i) sA[i * WTHREADS] = An[i];
+                for (int i = 0; i < WNP; ++i) {
 #pragma unroll
-                for (int i = 0; i < WNP; ++i) sg[i * WTHREADS] = gn[i];
+                    for (int k = 0; k <= i; ++k) sA[wtri(i, k) * WTHREADS] = An[wtri(i, k)] * (iS[i] * iS[k]);
+                    sg[i * WTHREADS] = gn[i];
+                }
             }
 
             if (status == 0) {
-                // ---------------------------------------------------------- lmpar (:2077-2190)
-                float L[WNT], Li[WNP], rhs[WNP], z[WNP];
+                // ---------------------------------------------------------- lmpar (:2077-2190), FP32
+                float L[WNT], Li[WNP], rhs[WNP], z[WNP], T[WNP], pf[WNP];
 #pragma unroll
-                for (int i = 0; i < WNP; ++i) rhs[i] = -sg[i * WTHREADS] * iS[i];
-                const unsigned ok = w_chol7(sA, iS, diag, 0.0f, L, Li, 16.0f * 1.1920929e-07f);
-                w_fwd7(L, Li, rhs, z);
-                w_bwd7(L, Li, z);
-                float pf[WNP];
-                float dx2f = 0.0f;
-#pragma unroll
-                for (int j = 0; j < WNP; ++j) { pf[j] = z[j] * iS[j]; const float t = diag[j] * pf[j]; dx2f = fmaf(t, t, dx2f); }
-                double dxnorm = sqrt((double)dx2f);
-                double fp = dxnorm - delta;
-                double par_used = 0.0;
-                if (fp > 0.1 * delta) {                                   // Gauss-Newton step too long (:2112)
-                    double parl = 0.0;
-                    if (ok == 0x7fu) {
-                        float u[WNP], w[WNP];
-                        const float idx_ = (float)(1.0 / dxnorm);
-#pragma unroll
-                        for (int j = 0; j < WNP; ++j) u[j] = diag[j] * diag[j] * iS[j] * pf[j] * idx_;
-                        w_fwd7(L, Li, u, w);
-                        float t2 = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < WNP; ++j) t2 = fmaf(w[j], w[j], t2);
-                        if (t2 > 0.0f) parl = (fp / delta) / (double)t2;
-                    }
-                    float gs2 = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < WNP; ++j) { const float t = sg[j * WTHREADS] / diag[j]; gs2 = fmaf(t, t, gs2); }
-                    const double gsn = sqrt((double)gs2);
-                    double paru = gsn / delta;
-                    if (paru == 0.0) paru = WQ_DWARF / fmin(delta, 0.1);
-                    double prr = fmin(fmax(par, parl), paru);
-                    if (prr == 0.0) prr = gsn / dxnorm;
+                for (int i = 0; i < WNP; ++i) { rhs[i] = -sg[i * WTHREADS]; const float t = diag[i] * iS[i]; T[i] = t * t; }
+                float prr = 0.0f, par_used = 0.0f, fp = 0.0f, parl = 0.0f, paru = 0.0f, dxnorm = 0.0f;
+                unsigned ok = 0;
 #pragma unroll 1
-                    for (int it = 0; it < 10; ++it) {
-                        if (prr == 0.0) prr = fmax(WQ_DWARF, paru * 0.001);
-                        w_chol7(sA, iS, diag, fmaxf((float)prr, 1e-30f), L, Li, 0.0f);
-                        w_fwd7(L, Li, rhs, z);
-                        w_bwd7(L, Li, z);
+                for (int it = 0; it <= 10; ++it) {
+                    const unsigned okk = w_chol7(sA, T, prr, L, Li, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f);
+                    if (it == 0) ok = okk;
+                    w_fwd7(L, Li, rhs, z);
+                    w_bwd7(L, Li, z);
+                    float dx2 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < WNP; ++j) { pf[j] = z[j] * iS[j]; const float t = diag[j] * pf[j]; dx2 = fmaf(t, t, dx2); }
+                    dxnorm = sqrtf(dx2);
+                    const float temp = fp;
+                    fp = dxnorm - delta;
+                    if (it == 0) {
+                        if (fp <= 0.1f * delta) break;                // Gauss-Newton step inside the region (:2112)
+                    } else {
                         ++n_damped;
-                        dx2f = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < WNP; ++j) { pf[j] = z[j] * iS[j]; const float t = diag[j] * pf[j]; dx2f = fmaf(t, t, dx2f); }
-                        dxnorm = sqrt((double)dx2f);
-                        const double temp = fp;
-                        fp = dxnorm - delta;
                         par_used = prr;
-                        if ((fabs(fp) <= 0.1 * delta) || ((parl == 0.0) && (fp <= temp) && (temp < 0.0)) || it == 9) break;
-                        float u[WNP], w[WNP];
-                        const float idx_ = (float)(1.0 / dxnorm);
-#pragma unroll
-                        for (int j = 0; j < WNP; ++j) u[j] = diag[j] * diag[j] * iS[j] * pf[j] * idx_;
-                        w_fwd7(L, Li, u, w);
-                        float t2 = 0.0f;
-#pragma unroll
-                        for (int j = 0; j < WNP; ++j) t2 = fmaf(w[j], w[j], t2);
-                        const double parc = (fp / delta) / (double)t2;
-                        if (fp > 0.0) parl = fmax(parl, prr);
-                        if (fp < 0.0) paru = fmin(paru, prr);
-                        prr = fmax(parl, prr + parc);
+                        if ((fabsf(fp) <= 0.1f * delta) || ((parl == 0.0f) && (fp <= temp) && (temp < 0.0f)) || it == 10) break;
                     }
+                    float u[WNP], w[WNP];
+                    const float idn = __fdividef(1.0f, dxnorm);
+#pragma unroll
+                    for (int j = 0; j < WNP; ++j) u[j] = T[j] * z[j] * idn;          // D^2 p / |D p| in scaled variables
+                    w_fwd7(L, Li, u, w);
+                    float t2 = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < WNP; ++j) t2 = fmaf(w[j], w[j], t2);
+                    const float parc = __fdividef(__fdividef(fp, delta), t2);
+                    if (it == 0) {
+                        parl = (ok == 0x7fu && t2 > 0.0f) ? parc : 0.0f;
+                        float gs2 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < WNP; ++j) { const float t = __fdividef(rhs[j], diag[j] * iS[j]); gs2 = fmaf(t, t, gs2); }
+                        const float gsn = sqrtf(gs2);
+                        paru = __fdividef(gsn, delta);
+                        if (paru == 0.0f) paru = __fdividef(WQ_TINYF, fminf(delta, 0.1f));
+                        prr = fminf(fmaxf(par, parl), paru);
+                        if (prr == 0.0f) prr = __fdividef(gsn, dxnorm);
+                    } else {
+                        if (fp > 0.0f) parl = fmaxf(parl, prr);
+                        if (fp < 0.0f) paru = fminf(paru, prr);
+                        prr = fmaxf(parl, prr + parc);
+                    }
+                    if (prr == 0.0f) prr = fmaxf(WQ_TINYF, paru * 0.001f);
                 }
                 par = par_used;
 
                 // ---------------------------------------------------------- bounds (:1184-1231)
-                double p[WNP];
-#pragma unroll
-                for (int j = 0; j < WNP; ++j) p[j] = (double)pf[j];
-                double alpha = 1.0;
                 {
-                    double mx = p[0], mn = p[0];
+                    float mx = pf[0], mn = pf[0];
 #pragma unroll
-                    for (int j = 1; j < WNP; ++j) { mx = fmax(mx, p[j]); mn = fmin(mn, p[j]); }
-#pragma unroll
-                    for (int j = 0; j < WNP; ++j) {
-                        if ((lpeg >> j) & 1u) p[j] = fmin(fmax(p[j], 0.0), mx);
-                        if ((upeg >> j) & 1u) p[j] = fmin(fmax(p[j], mn), 0.0);
-                    }
+                    for (int j = 1; j < WNP; ++j) { mx = fmaxf(mx, pf[j]); mn = fminf(mn, pf[j]); }
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) {
-                        if (fabs(p[j]) > WQ_MACHEP) {
-                            if (x[j] + p[j] < pf_lo(j, lo1)) alpha = fmin(alpha, (pf_lo(j, lo1) - x[j]) / p[j]);
-                            if (((PF_QUL >> j) & 1u) && (x[j] + p[j] > pf_hi(j))) alpha = fmin(alpha, (pf_hi(j) - x[j]) / p[j]);
-                        }
+                        if ((lpeg >> j) & 1u) pf[j] = fminf(fmaxf(pf[j], 0.0f), mx);
+                        if ((upeg >> j) & 1u) pf[j] = fminf(fmaxf(pf[j], mn), 0.0f);
                     }
                 }
-                double pn = 0.0;
+                // step scale that lands on the first bound hit: the ratio is formed in FP32 and nudged
+                // up by 3 ulp, so the limiting parameter overshoots its bound by a hair and is snapped
+                // onto it below (the reference reaches the bound to within machep and snaps likewise)
+                float alpha = 1.0f;
+#pragma unroll
+                for (int j = 0; j < WNP; ++j) {
+                    const double xn = x[j] + (double)pf[j];
+                    if (fabsf(pf[j]) > machep) {
+                        if (xn < pf_lo(j, lo1)) alpha = fminf(alpha, __fdividef((float)(pf_lo(j, lo1) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (((PF_QUL >> j) & 1u) && (xn > pf_hi(j))) alpha = fminf(alpha, __fdividef((float)(pf_hi(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                    }
+                }
+                float pn = 0.0f;
                 nonfinite = false;
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) {
-                    p[j] *= alpha;
-                    double xn = x[j] + p[j];
+                    pf[j] *= alpha;
+                    double xn = x[j] + (double)pf[j];
                     const double ll = pf_lo(j, lo1);
                     const double llim1 = ll * (1.0 + WQ_MACHEP) + ((ll == 0.0) ? WQ_MACHEP : 0.0);   // ll >= 0 here
                     if ((PF_QUL >> j) & 1u) {
@@ -498,40 +547,42 @@ lmwarp_kernel(const WarpArgs a) {
                     }
                     if (xn <= llim1) xn = ll;
                     y[j] = xn;
-                    pf[j] = (float)p[j];
-                    const double t = (double)diag[j] * p[j];
-                    pn += t * t;
-                    nonfinite |= !(isfinite(p[j]) && isfinite(xn));
+                    const float t = diag[j] * pf[j];
+                    pn = fmaf(t, t, pn);
+                    nonfinite |= !(isfinite(pf[j]) && isfinite(xn));
                 }
-                pnorm = sqrt(pn);
-                if (niter == 1) delta = fmin(delta, pnorm);                              // :1237-1238
-                float pAp = 0.0f;                                                        // |J p|^2
+                pnorm = sqrtf(pn);
+                if (niter == 1) delta = fminf(delta, pnorm);                             // :1237-1238
+                float pAp = 0.0f;                                                        // |J p|^2 = zs^T As zs, zs = p / iS
+                {
+                    float zs[WNP];
 #pragma unroll
-                for (int i = 0; i < WNP; ++i) {
-                    float s = 0.0f;
+                    for (int j = 0; j < WNP; ++j) zs[j] = __fdividef(pf[j], iS[j]);
 #pragma unroll
-                    for (int j = 0; j < WNP; ++j) s = fmaf(sA[((i >= j) ? wtri(i, j) : wtri(j, i)) * WTHREADS], pf[j], s);
-                    pAp = fmaf(s, pf[i], pAp);
+                    for (int i = 0; i < WNP; ++i) {
+                        float s = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < WNP; ++j) s = fmaf(sA[((i >= j) ? wtri(i, j) : wtri(j, i)) * WTHREADS], zs[j], s);
+                        pAp = fmaf(s, zs[i], pAp);
+                    }
                 }
                 // mpfit applies alpha to the (already scaled) step once more here (:1265)
-                const double t1sq = alpha * alpha * fmax((double)pAp, 0.0) / (fnorm * fnorm);
-                const double t2sq = alpha * par * pnorm * pnorm / (fnorm * fnorm);
-                prered = t1sq + t2sq / 0.5;
+                const float t1sq = alpha * alpha * fmaxf(pAp, 0.0f) * rss0;
+                const float t2sq = alpha * par * pnorm * pnorm * rss0;
+                prered = t1sq + 2.0f * t2sq;
                 dirder = -(t1sq + t2sq);
                 mode = MODE_TRIAL;
             } else {
                 // ---------------------------------------------------------- results (pflib.py:461-477)
                 if (status > 0) ++nfev;                                                  // :1351-1355
-                const double fn = fmax(fnorm, fnorm1);
                 double* o = a.out_fit + idx * 12;
                 const double sst = o[8];
-                const double ssr = fnorm * fnorm;                  // residual sum of squares at the final parameters
                 o[0] = (x[2] + (double)cand_h) - 2.5;                                    // pflib.py:461
                 o[1] = (x[3] + (double)cand_w) - 2.5;
                 o[2] = x[0]; o[3] = x[1]; o[4] = x[4]; o[5] = x[5]; o[6] = x[6];
-                o[7] = sqrt(ssr / 25.0); o[8] = 1.0 - ssr / sst;
-                o[10] = fn * fn;                                                         // mpfit .fnorm (:1357-1359)
-                o[11] = fnorm;
+                o[7] = sqrt(ss0 / 25.0); o[8] = 1.0 - ss0 / sst;   // ss0 = residual sum of squares at the final parameters
+                o[10] = fmax(ss0, ss1);                                                  // mpfit .fnorm (:1357-1359)
+                o[11] = sqrt(ss0);
                 *reinterpret_cast<int4*>(a.out_int + idx * 4) = make_int4(status, niter, nfev, n_damped);
                 active = false;
             }
