@@ -180,7 +180,7 @@ class ClockSampler(object):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -189,9 +189,12 @@ class ClockSampler(object):
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, windows=()):
+        """windows: (t0, t1) perf_counter intervals of the timed regions; samples inside them are
+        preferred, all samples of the run are the fall-back when the regions were shorter than the
+        sampling period."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -201,7 +204,12 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if any(a <= t <= b + 0.15 for a, b in windows)]
+        scope = "timed regions"
+        if len(inside) < 3:
+            inside = [ln for (_, ln) in self.lines]
+            scope = "whole GPU phase of the run (timed regions shorter than the sampling period)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -214,11 +222,20 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # --------------------------------------------------------------------------- our arm
+SOLVERS = {"fast": ("fast", False), "fast64": ("fast64", False),
+           "minpack-faithful": ("minpack", True), "minpack-clean": ("minpack", False)}
+# SURVEY.md 8(d) FLOP convention per executed LM iteration, P = 25 pixels, n = 7 parameters
+#   fast   : 1 evaluation (22 P) + analytic Jacobian (40 P) + J^T J, J^T r (70 P) + 7x7 damped solve (~300)
+#   minpack: 8 evaluations (176 P) + Householder QR (2 P n^2 - 2/3 n^3 = 2221) + Q^T f (4 P n) + lmpar (~10 x 350)
+FLOP_PER_LM_ITER = {"fast": 132 * 25 + 300, "fast64": 132 * 25 + 300, "minpack": FLOP_PER_LM_ITER_5x5}
+
+
 def run_ours(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     from fluorosequencingimageanalysis_b200 import engine, _lib
@@ -239,6 +256,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     L = _lib.load()
+    solver, faithful = SOLVERS[args.solver]
+    warmup = max(args.warmup, 3)
     # ---- synthetic inputs: N_VARIANTS different 40-frame stacks, host (pinned) and device copies
     stacks_host = []
     for v in range(N_VARIANTS):
@@ -246,39 +265,48 @@ def run_ours(args):
         t = torch.from_numpy(st.view(np.int16)).view(torch.uint16).pin_memory()
         stacks_host.append(t)
     stacks_dev = [t.to(dev) for t in stacks_host]
-    pipe = engine.FieldPipeline(N_FRAMES, H, W, dtype=torch.uint16, faithful=not args.clean)
-    pinned = pipe.pinned_buffers()
     in_bytes = N_FRAMES * H * W * 2
+    kw = dict(dtype=torch.uint16, faithful=faithful, solver=solver)
+    cur = torch.cuda.current_stream()
 
-    # ---- warm-up
-    for w in range(max(args.warmup, 3)):
-        pipe.run(stacks_dev[w % N_VARIANTS])
-    torch.cuda.synchronize()
-    n_probe = pipe.total()
+    # ---- timed region A: inputs resident in HBM; K steps software-pipelined over `depth` streams
+    fs = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=False, **kw)
+    totals = torch.zeros(max(args.steps, warmup), dtype=torch.int64, device=dev)
+    if args.park is not None:
+        kw["park_after"] = args.park
 
-    # ---- timed region A: inputs resident in HBM, K steps, CUDA events on the launching stream
+    def resident_steps(n_steps, first):
+        for k in range(n_steps):
+            sl = fs.submit(stacks_dev[(first + k) % N_VARIANTS])
+            with torch.cuda.stream(sl["stream"]):
+                totals[k].copy_(sl["pipe"].n_cand[sl["pipe"].F])          # device-side bookkeeping, no sync
+        for sl in fs.slots:
+            cur.wait_stream(sl["stream"])
+
     sampler = ClockSampler(local_rank)
     sampler.start()
+    resident_steps(warmup, 0)
+    torch.cuda.synchronize()
+    n_probe = int(totals[0].item())
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    totals = torch.zeros(args.steps, dtype=torch.int64, device=dev)
-    niters = torch.zeros(args.steps, dtype=torch.int64, device=dev)
     barrier()
+    win_a0 = time.perf_counter()
     ev[0].record()
-    for k in range(args.steps):
-        pipe.run(stacks_dev[(k + 3) % N_VARIANTS])
-        totals[k] = pipe.n_cand[pipe.F]                       # device-side bookkeeping, no sync
+    resident_steps(args.steps, 3)
     ev[1].record()
     barrier()
+    win_a1 = time.perf_counter()
     ms_total = ev[0].elapsed_time(ev[1])
-    clocks = sampler.stop()
-    fits_total = int(totals.sum().item())
-    if int(totals.max().item()) > pipe.cap:
+    fits_total = int(totals[:args.steps].sum().item())
+    pipe = fs.slots[0]["pipe"]
+    if int(totals[:args.steps].max().item()) > pipe.cap:
         raise RuntimeError("candidate capacity exceeded")
 
-    # ---- fit kernel alone (roofline): K launches re-fitting the last detection, events per launch
+    # ---- fit launches alone (roofline): re-fit the last detection of slot 0, events per launch
+    frames_k = stacks_dev[0]
+    pipe.run(frames_k)
     fit_ms = []
-    for k in range(max(3, min(args.steps, 8))):
-        frames_k = stacks_dev[(args.steps - 1 + 3) % N_VARIANTS]
+    for k in range(max(4, min(args.steps, 8))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pipe.run_fit_only(frames_k)
@@ -288,10 +316,10 @@ def run_ours(args):
     n_last = pipe.total()
     sum_niter = int(pipe.out_int[:n_last, engine.ICOL_NITER].sum().item())
     sum_nfev = int(pipe.out_int[:n_last, engine.ICOL_NFEV].sum().item())
-    fit_ms_avg = float(np.mean(fit_ms[1:])) if len(fit_ms) > 1 else float(fit_ms[0])
+    fit_ms_avg = float(np.mean(fit_ms[1:]))
     # detection alone
     det_ms = []
-    for k in range(4):
+    for k in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         pipe.run_detect_only(stacks_dev[(k + 5) % N_VARIANTS])
@@ -299,24 +327,58 @@ def run_ours(args):
         e1.synchronize()
         det_ms.append(e0.elapsed_time(e1))
     det_ms_avg = float(np.mean(det_ms[1:]))
+    # un-pipelined step (one stream, one batch at a time): what a single isolated call costs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(4):
+        pipe.run(stacks_dev[(k + 1) % N_VARIANTS])
+    e1.record()
+    e1.synchronize()
+    serial_ms_per_step = e0.elapsed_time(e1) / 4.0
 
-    # ---- timed region B (e2e): host pinned frames in, packed results back on the host, every step
-    for w in range(2):
-        d = stacks_host[w].to(dev, non_blocking=True)
-        pipe.run(d)
-        pipe.fetch(pinned)
+    # ---- timed region B (e2e): pinned host frames in, packed results back on the host, every step;
+    #      submit(k) / begin_fetch(k-1) / end_fetch(k-2) keeps H2D, kernels and D2H of neighbouring steps in flight
+    fe = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=True, **kw)
+
+    def e2e_steps(n_steps, first):
+        fits = d2h = 0
+        tick = []
+        for k in range(n_steps):
+            tick.append(fe.submit(stacks_host[(first + k) % N_VARIANTS]))
+            if k >= 1:
+                fe.begin_fetch(tick[k - 1])
+            if k >= 2:
+                n = fe.end_fetch(tick[k - 2])[0]
+                fits += n
+                d2h += pipe.d2h_bytes(n)
+        for t in tick[max(0, n_steps - 2):]:
+            n = fe.end_fetch(t)[0]
+            fits += n
+            d2h += pipe.d2h_bytes(n)
+        return fits, d2h
+
+    e2e_steps(3, 0)
     barrier()
     t0 = time.perf_counter()
-    e2e_fits = 0
-    d2h = 0
-    for k in range(args.steps):
-        d = stacks_host[(k + 2) % N_VARIANTS].to(dev, non_blocking=True)
-        pipe.run(d)
-        n, _, _, _, _ = pipe.fetch(pinned)
-        e2e_fits += n
-        d2h += pipe.d2h_bytes(n)
+    e2e_fits, d2h = e2e_steps(args.steps, 2)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop([(win_a0, win_a1), (t0, t0 + e2e_s)])
+
+    # ---- the parity instrument (reference-faithful MINPACK solver) on the same batch, 2 launches
+    parity = None
+    if rank == 0 and solver != "minpack" and not args.no_parity_solver:
+        pp = engine.FieldPipeline(N_FRAMES, H, W, dtype=torch.uint16, faithful=True, solver="minpack")
+        pp.run(frames_k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pp.run(frames_k)
+        e1.record()
+        e1.synchronize()
+        parity = {"solver": "minpack-faithful (reference behaviour incl. qrsolv diagonal view, FD Jacobian, QR)",
+                  "value": pp.total() / (e0.elapsed_time(e1) * 1e-3), "unit": "fits/s", "ms_per_step": e0.elapsed_time(e1)}
+        del pp
 
     # ---- max over ranks, sum of work
     if world > 1:
@@ -337,15 +399,16 @@ def run_ours(args):
 
     value = fits_all / (ms_total * 1e-3)
     frames_per_s = world * args.steps * N_FRAMES / (ms_total * 1e-3)
-    # ---- roofline of the dominant kernel (the LM fitter; FP64-pipe bound, never tensor cores)
+    # ---- roofline of the dominant kernel (the LM fitter; FP pipes, never tensor cores)
     peak = {}
     for nm, flag in (("fp64", 1), ("fp32", 0)):
-        import ctypes
         v = ctypes.c_double(0.0)
         _lib.check(L.fsq_fma_peak(flag, ctypes.byref(v), None))
         peak[nm] = v.value
-    flops = sum_niter * FLOP_PER_LM_ITER_5x5
+    fl_iter = FLOP_PER_LM_ITER[solver]
+    flops = sum_niter * fl_iter
     achieved = flops / (fit_ms_avg * 1e-3) / 1e12
+    pk = "fp64" if solver in ("minpack", "fast64") else "fp32"
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_file):
@@ -356,13 +419,18 @@ def run_ours(args):
             pass
     det_bytes = N_FRAMES * H * W * 2 + 8 * n_last
     det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak["fp64"] / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (peak["fp64"] / 1e12), "traffic": None,
-                "kernel": "lmfit_kernel<8,true> (fsq_fit_candidates)", "ms_per_launch": fit_ms_avg,
-                "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "nfev_per_launch": sum_nfev,
-                "flop_per_lm_iteration": FLOP_PER_LM_ITER_5x5,
-                "peak_source": "fsq_fma_peak FP64 FMA micro-benchmark, measured in this run (of measured)",
-                "fp32_fma_peak_tflops": peak["fp32"] / 1e12, "share_of_step": fit_ms_avg / (ms_total / args.steps)}
+    kname = {"fast": "lmwarp_kernel phase 1 + phase 2 (+ fit_prep_kernel) behind fsq_fit_candidates",
+             "fast64": "lmfast_kernel<double,true>", "minpack": "lmfit_kernel<8,true>"}[solver]
+    roofline = {"bound": pk, "achieved": achieved, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / (peak[pk] / 1e12), "traffic": None,
+                "kernel": kname, "ms_per_launch": fit_ms_avg,
+                "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "passes_per_launch": sum_nfev,
+                "flop_per_lm_iteration": fl_iter,
+                "peak_source": "fsq_fma_peak %s FMA micro-benchmark, measured in this run (of measured)" % pk.upper(),
+                "fp32_fma_peak_tflops": peak["fp32"] / 1e12, "fp64_fma_peak_tflops": peak["fp64"] / 1e12,
+                "share_of_serial_step": fit_ms_avg / serial_ms_per_step,
+                "note": "FLOPs by the SURVEY 8(d) convention; the kernel keeps residual/chi^2 in FP64 and the "
+                        "Jacobian / normal equations / Cholesky in FP32, so the FP32 peak is an upper bound it cannot reach"}
     roofline_detect = {"bound": "hbm", "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": det_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                        "kernels": "detect_cm + thr + rowmask + scans + emit", "ms_per_launch": det_ms_avg,
@@ -383,20 +451,22 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32" if solver == "fast" else "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots (sigma 1.5), every frame: "
                                "detection + 5x5 LM fit of every candidate + metrics",
                    "frames_per_step": N_FRAMES, "candidates_per_step": n_probe,
-                   "solver": "minpack-clean" if args.clean else "minpack-faithful (reference behaviour incl. qrsolv diagonal view)",
+                   "solver": args.solver, "pipeline_depth": args.depth,
                    "l2": "8 different stacks cycled (168 MB > 126 MB L2): inputs larger than L2", "parallelism": "field-sharded x%d, no collective" % world},
-        "frames_per_s": frames_per_s,
+        "frames_per_s": frames_per_s, "serial_ms_per_step": serial_ms_per_step,
         "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": d2h // max(args.steps, 1), "frames_per_s": world * args.steps * N_FRAMES / (e2e_ms * 1e-3),
-                "api": "engine.FieldPipeline.run + fetch over fsq_detect / fsq_fit_candidates (pinned host frames in, packed results out)"},
-        "gpu_launches": args.steps * pipe.kernels_per_run,
+                "api": "engine.FieldStream submit/begin_fetch/end_fetch over fsq_detect / fsq_fit_candidates (pinned host frames in, packed results out)"},
+        "gpu_launches": args.steps * fs.kernels_per_run,
         "clocks": clocks, "roofline": roofline, "roofline_detect": roofline_detect,
     }
+    if parity is not None:
+        line["parity_solver"] = parity
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -408,10 +478,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clean", action="store_true", help="clean-MINPACK solver instead of the reference-faithful one")
+    ap.add_argument("--solver", default="fast", choices=["fast", "fast64", "minpack-faithful", "minpack-clean"])
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (streams) in the pipelined regions")
+    ap.add_argument("--no-parity-solver", action="store_true")
+    ap.add_argument("--park", type=int, default=None, help="fsq_lm_opts.park_after override (scheduling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

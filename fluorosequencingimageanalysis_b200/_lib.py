@@ -18,7 +18,8 @@ FSQ_OK, FSQ_E_ARG, FSQ_E_CAPACITY, FSQ_E_CUDA, FSQ_E_RANGE = 0, -1, -2, -3, -4
 
 EXPORTED = ["fsq_version", "fsq_last_error", "fsq_detect_scratch_bytes", "fsq_detect",
             "fsq_detect_flags", "fsq_detect_copy_cm32", "fsq_lm_default_opts",
-            "fsq_gaussfit_batch", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_metrics", "fsq_photometry",
+            "fsq_gaussfit_batch", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
+            "fsq_metrics", "fsq_photometry",
             "fsq_fma_peak"]
 
 
@@ -26,7 +27,8 @@ class LmOpts(_c.Structure):
     """struct fsq_lm_opts (mpfit keyword defaults, agpy/mpfit/mpfit.py:600-605)."""
     _fields_ = [("ftol", _c.c_double), ("xtol", _c.c_double), ("gtol", _c.c_double),
                 ("factor", _c.c_double), ("maxiter", _c.c_int32), ("faithful", _c.c_int32),
-                ("want_perror", _c.c_int32), ("solver", _c.c_int32)]
+                ("want_perror", _c.c_int32), ("solver", _c.c_int32),
+                ("park_after", _c.c_int32), ("reserved", _c.c_int32)]
 
 
 class FsqError(RuntimeError):
@@ -70,7 +72,9 @@ def load():
                                            vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp]
     L.fsq_fit_candidates.restype = i32
     L.fsq_fit_candidates.argtypes = [vp, i32, i32, i32, i32, vp, vp, i64, vp, _c.POINTER(LmOpts),
-                                     vp, vp, vp, vp, vp]
+                                     vp, vp, vp, vp, i64, vp]
+    L.fsq_fit_scratch_bytes.restype = i64
+    L.fsq_fit_scratch_bytes.argtypes = [i64]
     L.fsq_metrics.restype = i32
     L.fsq_metrics.argtypes = [vp, vp, i64, vp, vp]
     L.fsq_photometry.restype = i32

@@ -24,6 +24,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # contraction: every fused operation in it is an explicit fma(), so its arithmetic is fixed by
 # the source (two template instantiations give bit-identical fits) -- DESIGN.md "Parity".
 EXTRA_FLAGS = {"fsq_lmfit.cu": ["-fmad=false"]}
+if os.environ.get("FSQ_WMINB"):          # developer knob: occupancy target of the FAST LM kernel
+    EXTRA_FLAGS["fsq_lmwarp.cu"] = ["-DWMINB=" + os.environ["FSQ_WMINB"]]
+if os.environ.get("FSQ_WDEFS"):          # developer knob: extra -D switches for the FAST LM kernel
+    EXTRA_FLAGS.setdefault("fsq_lmwarp.cu", []).extend(os.environ["FSQ_WDEFS"].split())
 
 
 def _nvcc():

@@ -139,6 +139,27 @@ photometry_kernel(const void* __restrict__ frames, int dtype, int H, int W,
     if (lane == 0) out[i] = res;
 }
 
+// ---- FMA-pipe micro-benchmark (roofline denominator of bench.py) -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
+    // 8 independent chains per thread, multiplier / addend read from memory so nothing folds
+    T a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = out[threadIdx.x] + (T)k;
+    const T b = out[1] + (T)1.0000001, c = out[2] + (T)1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+        }
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace fsq
 
 using namespace fsq;
@@ -171,5 +192,32 @@ extern "C" int fsq_photometry(const void* frames, int dtype_code, int n_frames, 
     photometry_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(frames, dtype_code, H, W, spots_hw,
                                                                                  spot_frame, n, method, radius, brim, out);
     FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
+
+extern "C" int fsq_fma_peak(int fp64, double* flops_out_host, void* stream) {
+    if (!flops_out_host) { set_error("fsq_fma_peak: NULL"); return FSQ_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
+    void* buf = nullptr;
+    FSQ_CUDA_CHECK(cudaMalloc(&buf, size_t(blocks) * threads * 8));
+    FSQ_CUDA_CHECK(cudaMemsetAsync(buf, 0, size_t(blocks) * threads * 8, st));
+    cudaEvent_t e0, e1;
+    FSQ_CUDA_CHECK(cudaEventCreate(&e0));
+    FSQ_CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        FSQ_CUDA_CHECK(cudaEventRecord(e0, st));
+        if (fp64) fma_peak_kernel<double><<<blocks, threads, 0, st>>>((double*)buf, iters);
+        else fma_peak_kernel<float><<<blocks, threads, 0, st>>>((float*)buf, iters);
+        FSQ_CUDA_CHECK(cudaEventRecord(e1, st));
+        FSQ_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        FSQ_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    const double flop = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
+    *flops_out_host = flop / (double(best) * 1e-3);
     return FSQ_OK;
 }

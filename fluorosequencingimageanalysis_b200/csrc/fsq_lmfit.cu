@@ -929,20 +929,6 @@ lmfit_kernel(const LmArgs a) {
 }
 
 // ---- FMA peak micro-benchmark (roofline denominator) --------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
-    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const T b = (T)0.999, c = (T)1e-4;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
-            a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
-
 static int launch_lm(const LmArgs& a, int G, bool pflib, cudaStream_t st) {
     const int groups_per_block = LM_THREADS / G;
     const size_t smem = sizeof(FitShared) * groups_per_block;
@@ -966,8 +952,8 @@ namespace fsq {
 // fsq_lmwarp.cu
 int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
-                        double* out_fit, int32_t* out_int, double* fit_img, unsigned long long* work_counter,
-                        cudaStream_t st);
+                        double* out_fit, int32_t* out_int, double* fit_img, void* scratch, cudaStream_t st);
+long long warp_scratch_bytes(long long n);
 // fsq_lmfast.cu
 int fast_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
@@ -984,7 +970,7 @@ using namespace fsq;
 extern "C" void fsq_lm_default_opts(fsq_lm_opts* o) {
     if (!o) return;
     o->ftol = 1e-10; o->xtol = 1e-10; o->gtol = 1e-10; o->factor = 100.0; o->maxiter = 200;   // mpfit.py:600-605
-    o->faithful = 1; o->want_perror = 0; o->solver = FSQ_SOLVER_MINPACK;
+    o->faithful = 1; o->want_perror = 0; o->solver = FSQ_SOLVER_MINPACK; o->park_after = 0; o->reserved = 0;
 }
 
 static int check_opts(const fsq_lm_opts* o, const char* who) {
@@ -1068,18 +1054,26 @@ extern "C" int fsq_gaussfit_batch_trace(const void* windows, int dtype_code, int
     return launch_lm(a, G, false, (cudaStream_t)stream);
 }
 
+extern "C" int64_t fsq_fit_scratch_bytes(int64_t n) { return (int64_t)warp_scratch_bytes(n); }
+
 extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_frames, int H, int W,
                                   const int32_t* cand_hw, const int32_t* cand_frame, int64_t n,
                                   const int64_t* n_dev, const fsq_lm_opts* opts, double* out_fit,
-                                  int32_t* out_int, double* fit_img, int64_t* work_counter, void* stream) {
+                                  int32_t* out_int, double* fit_img, void* scratch, int64_t scratch_bytes, void* stream) {
     int rc = check_opts(opts, "fsq_fit_candidates");
     if (rc) return rc;
     if (n < 0) { set_error("fsq_fit_candidates: n < 0"); return FSQ_E_ARG; }
     if (n == 0) return FSQ_OK;
-    if (!frames || !cand_hw || !cand_frame || !out_fit || !out_int || !work_counter) {
+    if (!frames || !cand_hw || !cand_frame || !out_fit || !out_int || !scratch) {
         set_error("fsq_fit_candidates: NULL pointer argument");
         return FSQ_E_ARG;
     }
+    if (scratch_bytes < fsq_fit_scratch_bytes(n)) {
+        set_error("fsq_fit_candidates: scratch of %lld bytes is smaller than fsq_fit_scratch_bytes(%lld) = %lld",
+                  (long long)scratch_bytes, (long long)n, (long long)fsq_fit_scratch_bytes(n));
+        return FSQ_E_CAPACITY;
+    }
+    int64_t* work_counter = (int64_t*)scratch;
     if (n_frames <= 0 || H < 5 || W < 5) { set_error("fsq_fit_candidates: bad frame shape"); return FSQ_E_ARG; }
     if (dtype_code != FSQ_U8 && dtype_code != FSQ_U16 && dtype_code != FSQ_I16 && dtype_code != FSQ_I32) {
         set_error("fsq_fit_candidates: unsupported frame dtype code %d", dtype_code);
@@ -1087,7 +1081,7 @@ extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_fram
     }
     if (opts->solver == FSQ_SOLVER_FAST)
         return warp_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
-                                   out_int, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);
+                                   out_int, fit_img, scratch, (cudaStream_t)stream);
     if (opts->solver != FSQ_SOLVER_MINPACK)
         return fast_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
                                    out_int, fit_img, (unsigned long long*)work_counter, (cudaStream_t)stream);
@@ -1100,28 +1094,3 @@ extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_fram
     return launch_lm(a, 8, true, (cudaStream_t)stream);
 }
 
-extern "C" int fsq_fma_peak(int fp64, double* flops_out_host, void* stream) {
-    if (!flops_out_host) { set_error("fsq_fma_peak: NULL"); return FSQ_E_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
-    void* buf = nullptr;
-    FSQ_CUDA_CHECK(cudaMalloc(&buf, size_t(blocks) * threads * 8));
-    cudaEvent_t e0, e1;
-    FSQ_CUDA_CHECK(cudaEventCreate(&e0));
-    FSQ_CUDA_CHECK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
-        FSQ_CUDA_CHECK(cudaEventRecord(e0, st));
-        if (fp64) fma_peak_kernel<double><<<blocks, threads, 0, st>>>((double*)buf, iters);
-        else fma_peak_kernel<float><<<blocks, threads, 0, st>>>((float*)buf, iters);
-        FSQ_CUDA_CHECK(cudaEventRecord(e1, st));
-        FSQ_CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms = 0;
-        FSQ_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) best = ms;
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
-    const double flop = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
-    *flops_out_host = flop / (double(best) * 1e-3);
-    return FSQ_OK;
-}

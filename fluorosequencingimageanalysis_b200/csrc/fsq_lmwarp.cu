@@ -40,6 +40,9 @@ namespace fsq {
 constexpr int WNP = 7;
 constexpr int WNT = 28;
 constexpr int WTHREADS = 128;
+#ifndef WMINB
+#define WMINB 3
+#endif
 #define WQ_MACHEP 2.220446049250313e-16
 #define WQ_DWARF 2.2250738585072014e-308
 #define WQ_DEG2RAD 0.017453292519943295
@@ -52,8 +55,25 @@ struct WarpArgs {
     long long n; const long long* n_dev;
     fsq_lm_opts o;
     double* out_fit; int32_t* out_int; double* fit_img;
-    unsigned long long* work_counter;
+    unsigned long long* work_counter;        // queue head of the running launch
+    unsigned long long* strag_count;         // number of parked fits (phase 1 appends, phase 2 consumes)
+    struct StragRec* strag;                  // parked fit states
+    int cap;                                 // phase 1: park a fit after this many passes (0 = never)
+    int resume;                              // phase 2: the work list is strag[0 .. *strag_count)
 };
+
+// State of a fit parked by phase 1 (everything the LM iteration carries from one accepted point
+// to the next; the normal equations are re-formed from x by the resuming launch, bit for bit).
+struct StragRec {
+    long long idx;
+    double x[7];
+    double ss0;
+    float diag[7];
+    float delta, par, xnorm;
+    int niter, nfev, n_damped;
+    int pad;
+};
+static_assert(sizeof(StragRec) == 128, "StragRec must be 128 bytes");
 
 __device__ __forceinline__ int w_ld_int(const void* base, int dtype, size_t off) {
     switch (dtype) {
@@ -281,10 +301,13 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     ss_out = ss;
 }
 
-enum { MODE_FIRST = 0, MODE_TRIAL = 1 };
+enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
 #define WQ_TINYF 1.0e-37f
+#ifndef WLMPAR_MAX
+#define WLMPAR_MAX 10      // lmpar iteration limit (mpfit.py:2148)
+#endif
 
-__global__ void __launch_bounds__(WTHREADS, 3)
+__global__ void __launch_bounds__(WTHREADS, WMINB)
 lmwarp_kernel(const WarpArgs a) {
     __shared__ double s_d[25 * WTHREADS];
     __shared__ float s_A[WNT * WTHREADS];      // column-scaled J^T J at the current point
@@ -300,6 +323,7 @@ lmwarp_kernel(const WarpArgs a) {
     const int maxiter = a.o.maxiter;
     long long n_total = a.n;
     if (a.n_dev) { const long long nd = *a.n_dev; n_total = nd < a.n ? nd : a.n; }
+    if (a.resume) { const long long ns = (long long)*a.strag_count; n_total = ns < n_total ? ns : n_total; }
 
     // ---- per-lane fit state
     bool active = false, exhausted = false;
@@ -325,9 +349,10 @@ lmwarp_kernel(const WarpArgs a) {
             if ((int)lane == leader) base = atomicAdd(a.work_counter, (unsigned long long)__popc(want));
             base = __shfl_sync(0xffffffffu, base, leader);
             if ((want >> lane) & 1u) {
-                idx = (long long)(base + (unsigned long long)__popc(want & ((1u << lane) - 1u)));
-                if (idx >= n_total) exhausted = true;
+                const long long slot = (long long)(base + (unsigned long long)__popc(want & ((1u << lane) - 1u)));
+                if (slot >= n_total) exhausted = true;
                 else {
+                    idx = a.resume ? a.strag[slot].idx : slot;
                     cand_h = a.cand_hw[2 * idx]; cand_w = a.cand_hw[2 * idx + 1];
                     const size_t fbase = (size_t)a.cand_frame[idx] * a.H * a.W + (size_t)(cand_h - 2) * a.W + (cand_w - 2);
 #pragma unroll 1
@@ -347,6 +372,14 @@ lmwarp_kernel(const WarpArgs a) {
                     }
                     active = true; mode = MODE_FIRST; status = 0; niter = 1; nfev = 0; n_damped = 0;
                     ss0 = -1.0; ss1 = -1.0; par = 0.0f; nonfinite = false;
+                    if (a.resume) {
+                        const StragRec* rec = a.strag + slot;
+#pragma unroll
+                        for (int j = 0; j < WNP; ++j) { x[j] = rec->x[j]; y[j] = x[j]; diag[j] = rec->diag[j]; }
+                        ss0 = rec->ss0; delta = rec->delta; par = rec->par; xnorm = rec->xnorm;
+                        niter = rec->niter; nfev = rec->nfev; n_damped = rec->n_damped;
+                        mode = MODE_RESUME;
+                    }
                 }
             }
         }
@@ -357,12 +390,14 @@ lmwarp_kernel(const WarpArgs a) {
             float An[WNT], gn[WNP];
             double ss;
             w_pass(y, sd, An, gn, ss);                      // y == x on the first tick of a fit
-            ++nfev;
+            if (mode != MODE_RESUME) ++nfev;
 
             bool have_new = false;
             if (mode == MODE_FIRST) {
                 ss0 = ss;                                                                // mpfit.py:999, :1019
                 have_new = true;
+            } else if (mode == MODE_RESUME) {
+                have_new = true;                            // same x, same arithmetic: ss == ss0 bit for bit
             } else {
                 // ---------------------------------------------------------- trial bookkeeping (:1245-1335)
                 ss1 = ss;
@@ -402,9 +437,21 @@ lmwarp_kernel(const WarpArgs a) {
                 }
                 if (status == 0 && !accepted && (nonfinite || !isfinite(ratio))) status = -16;   // :1330-1335
                 have_new = accepted;
+                if (status == 0 && accepted && a.cap > 0 && nfev >= a.cap) {
+                    // ------------------------------------------------------ park: a long fit leaves the lane
+                    StragRec* rec = a.strag + atomicAdd(a.strag_count, 1ull);
+                    rec->idx = idx;
+#pragma unroll
+                    for (int j = 0; j < WNP; ++j) { rec->x[j] = x[j]; rec->diag[j] = diag[j]; }
+                    rec->ss0 = ss0; rec->delta = delta; rec->par = par; rec->xnorm = xnorm;
+                    rec->niter = niter; rec->nfev = nfev; rec->n_damped = n_damped; rec->pad = 0;
+                    active = false;
+                }
             }
 
-            if (status == 0 && have_new) {
+            if (!active) {
+                // parked
+            } else if (status == 0 && have_new) {
                 // ---------------------------------------------------------- new linearisation at x
                 rss0 = __fdividef(1.0f, (float)ss0);
                 // pegged parameters: zero the column when the gradient pushes outwards (:1073-1091)
@@ -456,7 +503,9 @@ lmwarp_kernel(const WarpArgs a) {
                 }
             }
 
-            if (status == 0) {
+            if (!active) {
+                // parked
+            } else if (status == 0) {
                 // ---------------------------------------------------------- lmpar (:2077-2190), FP32
                 float L[WNT], Li[WNP], rhs[WNP], z[WNP], T[WNP], pf[WNP];
 #pragma unroll
@@ -464,7 +513,7 @@ lmwarp_kernel(const WarpArgs a) {
                 float prr = 0.0f, par_used = 0.0f, fp = 0.0f, parl = 0.0f, paru = 0.0f, dxnorm = 0.0f;
                 unsigned ok = 0;
 #pragma unroll 1
-                for (int it = 0; it <= 10; ++it) {
+                for (int it = 0; it <= WLMPAR_MAX; ++it) {
                     const unsigned okk = w_chol7(sA, T, prr, L, Li, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f);
                     if (it == 0) ok = okk;
                     w_fwd7(L, Li, rhs, z);
@@ -480,7 +529,7 @@ lmwarp_kernel(const WarpArgs a) {
                     } else {
                         ++n_damped;
                         par_used = prr;
-                        if ((fabsf(fp) <= 0.1f * delta) || ((parl == 0.0f) && (fp <= temp) && (temp < 0.0f)) || it == 10) break;
+                        if ((fabsf(fp) <= 0.1f * delta) || ((parl == 0.0f) && (fp <= temp) && (temp < 0.0f)) || it == WLMPAR_MAX) break;
                     }
                     float u[WNP], w[WNP];
                     const float idn = __fdividef(1.0f, dxnorm);
@@ -613,16 +662,19 @@ fit_image_kernel(const WarpArgs a) {
     }
 }
 
+long long warp_scratch_bytes(long long n) { return 64 + (long long)sizeof(StragRec) * (n > 0 ? n : 0); }
+
 int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
-                        double* out_fit, int32_t* out_int, double* fit_img, unsigned long long* work_counter,
-                        cudaStream_t st) {
+                        double* out_fit, int32_t* out_int, double* fit_img, void* scratch, cudaStream_t st) {
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = frames; a.fdtype = dtype_code; a.H = H; a.W = W; a.cand_hw = cand_hw; a.cand_frame = cand_frame;
     a.n = n; a.n_dev = n_dev; a.o = *opts; a.out_fit = out_fit; a.out_int = out_int; a.fit_img = fit_img;
-    a.work_counter = work_counter;
+    unsigned long long* head = (unsigned long long*)scratch;          // [0] queue head, [1] parked count
+    a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);
     const unsigned flat = (unsigned)((n + 127) / 128);
+    FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     fit_prep_kernel<<<flat, 128, 0, st>>>(a);
     FSQ_LAUNCH_CHECK();
     static int per_sm = 0;
@@ -634,9 +686,19 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     long long blocks = (long long)sm_count() * per_sm;
     const long long need = (n + WTHREADS - 1) / WTHREADS;
     if (need < blocks) blocks = need < 1 ? 1 : need;
-    FSQ_CUDA_CHECK(cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st));
+    // phase 1: every fit, parked after `cap` passes; phase 2: the parked fits to the end
+    a.cap = opts->park_after > 0 ? opts->park_after : 0; a.resume = 0;
     lmwarp_kernel<<<(unsigned)blocks, WTHREADS, 0, st>>>(a);
     FSQ_LAUNCH_CHECK();
+    if (a.cap > 0) {
+        FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
+        a.cap = 0; a.resume = 1;
+        // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
+        // whatever the caller has queued on other streams (the next batch's detection and phase 1)
+        const long long blocks2 = blocks < sm_count() ? blocks : sm_count();
+        lmwarp_kernel<<<(unsigned)blocks2, WTHREADS, 0, st>>>(a);
+        FSQ_LAUNCH_CHECK();
+    }
     if (fit_img) {
         fit_image_kernel<<<flat, 128, 0, st>>>(a);
         FSQ_LAUNCH_CHECK();

@@ -163,12 +163,13 @@ def fit_candidates(frames, cand_hw, cand_frame, n, faithful=True, want_fit_img=F
     out_fit = torch.empty((n, 12), dtype=torch.float64, device=dev)
     out_int = torch.empty((n, 4), dtype=torch.int32, device=dev)
     fit_img = torch.empty((n, 25), dtype=torch.float64, device=dev) if want_fit_img else None
-    counter = torch.zeros(1, dtype=torch.int64, device=dev)
     if n == 0:
         return out_fit, out_int, fit_img
+    sbytes = L.fsq_fit_scratch_bytes(n)
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
     rc = L.fsq_fit_candidates(_ptr(frames), _TORCH_DTYPE_CODE[frames.dtype], F, H, W, _ptr(cand_hw),
                               _ptr(cand_frame), n, _ptr(n_dev), ctypes.byref(o), _ptr(out_fit),
-                              _ptr(out_int), _ptr(fit_img), _ptr(counter), _stream())
+                              _ptr(out_int), _ptr(fit_img), _ptr(scratch), sbytes, _stream())
     _lib.check(rc)
     return out_fit, out_int, fit_img
 
@@ -329,7 +330,7 @@ class FieldPipeline(object):
 
     def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
                  median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
-                 device=None, solver="minpack"):
+                 device=None, solver="fast", park_after=None):
         require_cuda()
         self.L = _lib.load()
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -341,7 +342,7 @@ class FieldPipeline(object):
         self.K = _check_kernel(correlation_matrix)
         self.mf = int(median_filter_size)
         self.c_std = float(c_std)
-        self.opts = _lib.default_opts(faithful=faithful, solver=solver)
+        self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after)
         self.solver = solver
         if cap_per_frame is None:
             cap_per_frame = max(1024, int(0.06 * H * W))
@@ -355,9 +356,10 @@ class FieldPipeline(object):
         self.thr = torch.empty(self.F, dtype=torch.float64, device=d)
         self.out_fit = torch.empty((self.cap, 12), dtype=torch.float64, device=d)
         self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
-        self.counter = torch.zeros(1, dtype=torch.int64, device=d)
-        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (2 for the mixed solver)
-        self.kernels_per_run = 6 + (2 if _lib.SOLVERS[solver] == 2 else 1)
+        self.fit_sbytes = self.L.fsq_fit_scratch_bytes(self.cap)
+        self.fit_scratch = torch.empty(self.fit_sbytes, dtype=torch.uint8, device=d)
+        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (FAST: prep, phase 1, phase 2 when parking)
+        self.kernels_per_run = 6 + ((2 + (1 if self.opts.park_after > 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
 
     def run(self, frames_dev, fit=True):
         """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype)."""
@@ -373,7 +375,7 @@ class FieldPipeline(object):
             _lib.check(L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
                                             _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
                                             ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
-                                            None, _ptr(self.counter), st))
+                                            None, _ptr(self.fit_scratch), self.fit_sbytes, st))
 
     def run_detect_only(self, frames_dev):
         self.run(frames_dev, fit=False)
@@ -384,7 +386,7 @@ class FieldPipeline(object):
         _lib.check(self.L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
                                              _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
                                              ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
-                                             None, _ptr(self.counter), _stream()))
+                                             None, _ptr(self.fit_scratch), self.fit_sbytes, _stream()))
 
     def total(self):
         """Synchronising read of the candidate total; raises if the capacity was exceeded."""
@@ -414,3 +416,77 @@ class FieldPipeline(object):
 
     def d2h_bytes(self, n):
         return n * (12 * 8 + 4 * 4 + 2 * 4 + 4)
+
+
+class FieldStream(object):
+    """Software-pipelined production path: ``depth`` FieldPipeline slots, each on its own CUDA
+    stream with its own device and pinned host buffers, so that the host->device copy of batch
+    k+1, the kernels of batch k and the device->host copy of batch k-1 overlap -- and so that the
+    latency-bound tail of one batch's long fits runs underneath the next batch's bulk.
+
+        t = fs.submit(frames)          # pinned host tensor [F,H,W] (copied in) or a device tensor
+        fs.begin_fetch(t)              # waits for the candidate count, queues the D2H of exactly n rows
+        n, hw, frame, fit, ints = fs.end_fetch(t)     # views into the slot's pinned buffers
+
+    Call order for full overlap: submit(k); begin_fetch(k-1); end_fetch(k-2).  A slot is reused
+    after ``depth`` submits; its previous results must have been fetched (or abandoned) by then."""
+
+    def __init__(self, n_frames, H, W, dtype=None, depth=3, host_io=True, **kw):
+        require_cuda()
+        self.depth = int(depth)
+        self.slots = []
+        self.host_io = host_io
+        for _ in range(self.depth):
+            p = FieldPipeline(n_frames, H, W, dtype=dtype, **kw)
+            sl = {"pipe": p, "stream": torch.cuda.Stream(device=p.dev),
+                  "ev_count": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "n": None}
+            if host_io:
+                sl["frames_dev"] = torch.empty((p.F, p.H, p.W), dtype=p.dtype, device=p.dev)
+                sl["pinned"] = p.pinned_buffers()
+                sl["count_host"] = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self.slots.append(sl)
+        self.k = 0
+        self.kernels_per_run = self.slots[0]["pipe"].kernels_per_run
+
+    def submit(self, frames):
+        sl = self.slots[self.k % self.depth]
+        self.k += 1
+        p = sl["pipe"]
+        sl["stream"].wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(sl["stream"]):
+            if frames.device.type == "cpu":
+                sl["frames_dev"].copy_(frames, non_blocking=True)
+                frames = sl["frames_dev"]
+            p.run(frames)
+            if self.host_io:
+                sl["count_host"].copy_(p.n_cand[p.F:p.F + 1], non_blocking=True)
+                sl["ev_count"].record(sl["stream"])
+        sl["n"] = None
+        return sl
+
+    def begin_fetch(self, sl):
+        p = sl["pipe"]
+        sl["ev_count"].synchronize()
+        n = int(sl["count_host"][0])
+        if n > p.cap:
+            raise _lib.FsqError("capacity: %d candidates > cap %d; enlarge cap_per_frame" % (n, p.cap))
+        pin = sl["pinned"]
+        with torch.cuda.stream(sl["stream"]):
+            pin["fit"][:n].copy_(p.out_fit[:n], non_blocking=True)
+            pin["ints"][:n].copy_(p.out_int[:n], non_blocking=True)
+            pin["hw"][:n].copy_(p.cand_hw[:n], non_blocking=True)
+            pin["frame"][:n].copy_(p.cand_frame[:n], non_blocking=True)
+            sl["ev_done"].record(sl["stream"])
+        sl["n"] = n
+        return n
+
+    def end_fetch(self, sl):
+        if sl["n"] is None:
+            self.begin_fetch(sl)
+        sl["ev_done"].synchronize()
+        n, pin = sl["n"], sl["pinned"]
+        return n, pin["hw"][:n], pin["frame"][:n], pin["fit"][:n], pin["ints"][:n]
+
+    def synchronize(self):
+        for sl in self.slots:
+            sl["stream"].synchronize()

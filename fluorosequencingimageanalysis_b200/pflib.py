@@ -22,6 +22,14 @@ default_correlation_matrix = DEFAULT_CORRELATION_MATRIX.copy()      # pflib.py:4
 #: diagonal-view behaviour
 FAITHFUL = True
 
+#: which LM kernel the drop-in entry points run (fsq.h FSQ_SOLVER_*):
+#:   "minpack" -- the reference's algorithm operation for operation (with FAITHFUL: bug for bug);
+#:                this is what makes ``find_peptides`` return what the reference returns
+#:   "fast"    -- the production fitter (analytic Jacobian, normal equations; ~250x faster): equal to
+#:                the reference wherever the reference's own trajectory is a clean Gauss-Newton one,
+#:                a lower chi^2 elsewhere (DESIGN.md "Parity")
+SOLVER = "minpack"
+
 
 def _py2_round(x):
     """Python-2 round(): half away from zero (pflib.py:515)."""
@@ -68,7 +76,8 @@ def _fit_2d_gaussian(subimage, implementation='agpy'):
         raise NotImplementedError("Currently, only agpy is supported.")
     sub = subimage.astype(np.int64)[None] if subimage.dtype.kind in "iub" else subimage.astype(np.float64)[None]
     p0, lo, hi, lim_lo, lim_hi = _pflib_limits(sub)
-    r = engine.gaussfit_batch(sub, p0, lo, hi, lim_lo, lim_hi, faithful=FAITHFUL, want_fit_img=True)
+    r = engine.gaussfit_batch(sub, p0, lo, hi, lim_lo, lim_hi, faithful=FAITHFUL, want_fit_img=True,
+                              solver="minpack" if SOLVER == "minpack" else "fast64")
     H, A, h_0, w_0, sigma_h, sigma_w, theta = (float(v) for v in r.params[0].cpu().numpy())
     return (h_0, w_0, H, A, sigma_h, sigma_w, theta, r.fit_img[0].cpu().numpy())
 
@@ -147,7 +156,7 @@ def find_peptides(image, median_filter_size=5, correlation_matrix=default_correl
         raise NotImplementedError("fit_type='monte_carlo' (pflib.py:117-177) is not part of the CUDA hot path")
     image = np.asarray(image)
     res = engine.find_peptides_batch(image, median_filter_size, correlation_matrix, c_std,
-                                     faithful=FAITHFUL, want_fit_img=True)
+                                     faithful=FAITHFUL, want_fit_img=True, solver=SOLVER)
     keys, idx = consolidate_packed(res.cand_hw, res.fit, image.shape, r_2_threshold, consolidation_radius)
     out = {}
     for (kh, kw), i in zip(keys, idx):

@@ -96,6 +96,12 @@ typedef struct fsq_lm_opts {
                               (mpfit.py:1915,1956,1976-1977); 0: clean MINPACK            */
     int32_t want_perror;/* 1: compute covariance -> perror (mpfit.py:1361-1388); MINPACK solver only */
     int32_t solver;     /* FSQ_SOLVER_*                                                    */
+    int32_t park_after; /* FAST solver scheduling only (results do not depend on it): a fit that
+                           has not ended after this many passes over its window is parked and
+                           finished by a second launch over the parked fits, so that a handful of
+                           100+-iteration fits do not pin whole thread blocks.  0 = one launch
+                           (default; on B200 the two-launch schedule measured no faster).   */
+    int32_t reserved;
 } fsq_lm_opts;
 
 /* Solvers behind the two fit entry points.
@@ -161,13 +167,16 @@ int fsq_gaussfit_batch_trace(const void* windows, int dtype_code, int64_t n, int
  *              pflib.py:461), rmse, r_2, s_n, chi2, (reserved)
  *  out_int     [n, 4] int32: status, niter, nfev, n_qrsolv
  *  fit_img     [n, 25] float64 or NULL
- *  work_counter device int64 used as the work-queue head; the call zeroes it
+ *  scratch     device scratch of at least fsq_fit_scratch_bytes(n) bytes (work-queue head +
+ *              the states of parked fits); the call initialises it
  * ------------------------------------------------------------------------------------------ */
 int fsq_fit_candidates(const void* frames, int dtype_code, int n_frames, int H, int W,
                        const int32_t* cand_hw, const int32_t* cand_frame, int64_t n,
                        const int64_t* n_dev /* optional device count (n_cand total); NULL = use n */,
                        const fsq_lm_opts* opts, double* out_fit, int32_t* out_int,
-                       double* fit_img, int64_t* work_counter, void* stream);
+                       double* fit_img, void* scratch, int64_t scratch_bytes, void* stream);
+
+int64_t fsq_fit_scratch_bytes(int64_t n);
 
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */

@@ -84,7 +84,13 @@ def test_argument_validation_without_gpu():
     assert L.fsq_gaussfit_batch(one, _lib.FSQ_F64, 0, 5, one, one, one, one, one, ctypes.byref(o),
                                 one, null, one, one, one, one, null, null, one, null) == 0   # empty batch
     assert L.fsq_fit_candidates(one, _lib.FSQ_U16, 1, 8, 8, one, one, 0, null, ctypes.byref(o), one, one,
-                                null, one, null) == 0
+                                null, one, 64, null) == 0
+    # scratch smaller than fsq_fit_scratch_bytes(n) is refused before anything is launched
+    assert L.fsq_fit_scratch_bytes(0) == 64 and L.fsq_fit_scratch_bytes(1000) == 64 + 128 * 1000
+    rc = L.fsq_fit_candidates(one, _lib.FSQ_U16, 1, 8, 8, one, one, 10, null, ctypes.byref(o), one, one,
+                              null, one, 64, null)
+    assert rc == _lib.FSQ_E_CAPACITY and "scratch" in _lib.last_error()
+    assert o.park_after == 0 and ctypes.sizeof(_lib.LmOpts) == 56
     rc = L.fsq_photometry(one, _lib.FSQ_U16, 1, 8, 8, one, one, 1, 7, 9, 6, one, null)
     assert rc == _lib.FSQ_E_ARG and "method" in _lib.last_error()         # flexlibrary.py:315
     assert L.fsq_detect_scratch_bytes(0, 8, 8) == 0
