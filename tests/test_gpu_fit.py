@@ -278,7 +278,8 @@ def test_exact_gaussian_is_recovered():
         assert (r.status.cpu().numpy() > 0).all()
         good = agree(P, truth, tol=1e-6, ctol=1e-6)
         assert good.mean() > 0.93          # the rest end on another branch of the theta box
-        assert np.abs(r.fit_img.cpu().numpy()[good] - wins[good]).max() < 1e-4
+        # parameters within 1e-6 relative of the truth => model image within ~1e-5 of the peak value
+        assert np.abs(r.fit_img.cpu().numpy()[good] - wins[good]).max() < 1e-5 * wins.max()
 
 
 def test_start_outside_limits_gives_status_zero():
