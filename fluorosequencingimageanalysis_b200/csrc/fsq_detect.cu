@@ -13,6 +13,7 @@
 // Algorithmic bytes per frame: H*W*sizeof(pixel) read + 8*N_cand written.
 #include "fsq_common.cuh"
 #include "fsq_median.cuh"
+#include <stdlib.h>
 
 namespace fsq {
 
@@ -177,6 +178,145 @@ detect_cm_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp, int s
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Fast path of pass A for unsigned 8/16-bit pixels, 5x5 median, 5x5 template (the defaults).
+//   * the raw tile is staged as packed u16 pairs;
+//   * every thread computes the medians of TWO horizontally adjacent pixels at once: element
+//     (i, j) of both windows sits in one 32-bit register (byte-permuted from aligned words) and
+//     the 99-comparator network runs on __vminu2 / __vmaxu2, one instruction per pair;
+//   * mf = v - min(med, v) is one saturating packed subtract;
+//   * RING templates (pflib.default_correlation_matrix: border ring kr, inner ring ki, centre
+//     kc) use  cm = kr*S25 + (ki-kr)*S9 + (kc-ki)*c  with the 5x5 / 3x3 box sums slid down a
+//     column strip in registers; any other 5x5 template takes the 25-tap int64 form.
+// Same integers as the generic kernel (tests/test_gpu_detect.py compares both with the oracle).
+// -------------------------------------------------------------------------------------------
+struct U16x2 { unsigned v; };
+__device__ __forceinline__ U16x2 min(U16x2 a, U16x2 b) { U16x2 r; r.v = __vminu2(a.v, b.v); return r; }
+__device__ __forceinline__ U16x2 max(U16x2 a, U16x2 b) { U16x2 r; r.v = __vmaxu2(a.v, b.v); return r; }
+
+constexpr int PTW = 64, PTH = 32;                 // output tile
+constexpr int PRW = PTW + 8, PRH = PTH + 8;       // raw tile (halo 4), PRW even
+constexpr int PMW = PTW + 4, PMH = PTH + 4;       // mf tile (halo 2)
+constexpr int PSTRIP = 8;                         // output rows per thread in the correlation stage
+
+template <typename PixT, bool RING>
+__global__ void __launch_bounds__(NT)
+detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp,
+                        uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned raw2[PRH * (PRW / 2)];        // u16 pairs
+    __shared__ __align__(16) unsigned short mf[PMH * PMW];
+    __shared__ unsigned long long red[4][NT / 32];
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int ty0 = blockIdx.y * PTH, tx0 = blockIdx.x * PTW;
+    const PixT* img = frames + size_t(frame) * H * W;
+
+    // stage the raw tile (reflected at the image border), two pixels per word
+    for (int idx = tid; idx < PRH * (PRW / 2); idx += NT) {
+        const int ry = idx / (PRW / 2), rx = (idx - ry * (PRW / 2)) * 2;
+        const int gy = reflect_idx(ty0 - 4 + ry, H);
+        const int gx0 = reflect_idx(tx0 - 4 + rx, W), gx1 = reflect_idx(tx0 - 4 + rx + 1, W);
+        const unsigned lo = (unsigned)img[size_t(gy) * W + gx0], hi = (unsigned)img[size_t(gy) * W + gx1];
+        raw2[idx] = lo | (hi << 16);
+    }
+    __syncthreads();
+
+    // background removal for pixel pairs: mf = v - min(median, v); zero outside the image
+    for (int idx = tid; idx < PMH * (PMW / 2); idx += NT) {
+        const int my = idx / (PMW / 2), mx = (idx - my * (PMW / 2)) * 2;      // mf coords of the pair's first pixel
+        U16x2 p[25];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const unsigned* row = raw2 + (my + i) * (PRW / 2) + (mx >> 1);     // raw col = mx .. mx+5
+            const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
+            p[i * 5 + 0].v = w0;
+            p[i * 5 + 1].v = __byte_perm(w0, w1, 0x5432);
+            p[i * 5 + 2].v = w1;
+            p[i * 5 + 3].v = __byte_perm(w1, w2, 0x5432);
+            p[i * 5 + 4].v = w2;
+        }
+        const unsigned v = p[12].v;
+        const U16x2 med = median25<U16x2>(p);
+        unsigned out = __vsubus2(v, med.v);                                    // max(v - med, 0) per half
+        const int gy = ty0 - 2 + my, gx = tx0 - 2 + mx;
+        const bool yok = (gy >= 0) && (gy < H);
+        if (!(yok && gx >= 0 && gx < W)) out &= 0xffff0000u;
+        if (!(yok && gx + 1 >= 0 && gx + 1 < W)) out &= 0x0000ffffu;
+        *reinterpret_cast<unsigned*>(mf + my * PMW + mx) = out;
+    }
+    __syncthreads();
+
+    // correlation down column strips, clamp, store, exact moments
+    unsigned long long s1 = 0, saa = 0, sab = 0, sbb = 0, bad = 0;
+    {
+        const int ox = tid & (PTW - 1);                // 64 columns
+        const int oy0 = (tid / PTW) * PSTRIP;          // 4 strips of 8 rows
+        const int gx = tx0 + ox;
+        if (RING) {
+            const long long kr = kp.k[0], kd1 = (long long)kp.k[6] - kp.k[0], kd2 = (long long)kp.k[12] - kp.k[6];
+            int h5[5], h3[5];                          // row sums of the 5 rows under the window
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned short* r = mf + (oy0 + i) * PMW + ox;
+                const int m1 = r[1] + r[2] + r[3];
+                h3[i] = m1; h5[i] = m1 + r[0] + r[4];
+            }
+#pragma unroll
+            for (int q = 0; q < PSTRIP; ++q) {
+                const unsigned short* r = mf + (oy0 + q + 4) * PMW + ox;
+                const int m1 = r[1] + r[2] + r[3];
+                h3[(q + 4) % 5] = m1; h5[(q + 4) % 5] = m1 + r[0] + r[4];
+                const int S25 = h5[0] + h5[1] + h5[2] + h5[3] + h5[4];
+                const int S9 = h3[(q + 1) % 5] + h3[(q + 2) % 5] + h3[(q + 3) % 5];
+                const int c = mf[(oy0 + q + 2) * PMW + ox + 2];
+                const long long acc = kr * S25 + kd1 * S9 + kd2 * c;
+                const int gy = ty0 + oy0 + q;
+                if (gy < H && gx < W) {
+                    const unsigned long long cm = acc > 0 ? (unsigned long long)acc : 0ull;
+                    cm32[(size_t(frame) * H + gy) * W + gx] = cm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cm;
+                    const unsigned long long a = cm >> CM_SPLIT, b = cm & ((1ull << CM_SPLIT) - 1);
+                    bad |= (a >> 21);
+                    s1 += cm; saa += a * a; sab += a * b; sbb += b * b;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < PSTRIP; ++q) {
+                const int oy = oy0 + q, gy = ty0 + oy;
+                if (gy < H && gx < W) {
+                    long long acc = 0;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i)
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+                            acc += (long long)kp.k[i * 5 + j] * (long long)mf[(oy + i) * PMW + ox + j];
+                    const unsigned long long cm = acc > 0 ? (unsigned long long)acc : 0ull;
+                    cm32[(size_t(frame) * H + gy) * W + gx] = cm > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cm;
+                    const unsigned long long a = cm >> CM_SPLIT, b = cm & ((1ull << CM_SPLIT) - 1);
+                    bad |= (a >> 21);
+                    s1 += cm; saa += a * a; sab += a * b; sbb += b * b;
+                }
+            }
+        }
+    }
+    unsigned long long v[4] = {s1, saa, sab, sbb};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], m);
+        if ((tid & 31) == 0) red[q][tid >> 5] = v[q];
+    }
+    bad = __any_sync(0xffffffffu, bad != 0);
+    if (bad && (tid & 31) == 0) atomicOr(&sums[size_t(frame) * NSUM + 4], 1ull);
+    __syncthreads();
+    if (tid < 4) {
+        unsigned long long t = 0;
+        for (int w = 0; w < NT / 32; ++w) t += red[tid][w];
+        atomicAdd(&sums[size_t(frame) * NSUM + tid], t);
+    }
+}
+
 __global__ void detect_thr_kernel(const unsigned long long* __restrict__ sums, int F, long long N,
                                   double c_std, double* __restrict__ thr, int32_t* flags) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,11 +443,30 @@ detect_emit_kernel(const uint32_t* __restrict__ masks, const int32_t* __restrict
     }
 }
 
+static bool is_ring_template(const KParam& kp) {
+    // border ring = k[0], inner ring = k[6], centre = k[12] (pflib.default_correlation_matrix, pflib.py:48-52)
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 5; ++j) {
+            const bool border = (i == 0 || i == 4 || j == 0 || j == 4);
+            const bool centre = (i == 2 && j == 2);
+            const int want = border ? kp.k[0] : centre ? kp.k[12] : kp.k[6];
+            if (kp.k[i * 5 + j] != want) return false;
+        }
+    return true;
+}
+
 template <typename PixT>
 static int launch_cm(const void* frames, int F, int H, int W, const KParam& kp, int s, int k,
-                     const DetectScratch& sc, cudaStream_t st) {
+                     const DetectScratch& sc, cudaStream_t st, bool allow_packed) {
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, F);
-    if (s == 5 && k == 5)
+    constexpr bool kPackable = (sizeof(PixT) <= 2) && (PixT(-1) > PixT(0));      // u8, u16
+    if (kPackable && allow_packed && s == 5 && k == 5) {
+        static_assert(PTW == TW && PTH == TH, "tile shapes of the two pass-A kernels must agree");
+        if (is_ring_template(kp))
+            detect_cm_packed_kernel<PixT, true><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
+        else
+            detect_cm_packed_kernel<PixT, false><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
+    } else if (s == 5 && k == 5)
         detect_cm_kernel<PixT, 5, 5><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, s, k, sc.cm32, sc.sums);
     else
         detect_cm_kernel<PixT, 0, 0><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, s, k, sc.cm32, sc.sums);
@@ -365,14 +524,16 @@ extern "C" int fsq_detect(const void* frames, int dtype_code, int n_frames, int 
     DetectScratch sc;
     carve(&sc, (char*)scratch, n_frames, H, W);
     cudaStream_t st = (cudaStream_t)stream;
+    // developer switch (tests): FSQ_DETECT_GENERIC=1 forces the scalar pass-A kernel
+    static const bool allow_packed = !(getenv("FSQ_DETECT_GENERIC") && getenv("FSQ_DETECT_GENERIC")[0] == '1');
     FSQ_CUDA_CHECK(cudaMemsetAsync(sc.sums, 0, size_t(n_frames) * NSUM * 8, st));
     FSQ_CUDA_CHECK(cudaMemsetAsync(sc.flags, 0, 64, st));
     int rc;
     switch (dtype_code) {
-        case FSQ_U8:  rc = launch_cm<uint8_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
-        case FSQ_U16: rc = launch_cm<uint16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
-        case FSQ_I16: rc = launch_cm<int16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
-        case FSQ_I32: rc = launch_cm<int32_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st); break;
+        case FSQ_U8:  rc = launch_cm<uint8_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
+        case FSQ_U16: rc = launch_cm<uint16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
+        case FSQ_I16: rc = launch_cm<int16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
+        case FSQ_I32: rc = launch_cm<int32_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
         default:
             set_error("fsq_detect: unsupported dtype code %d", dtype_code);
             return FSQ_E_ARG;
