@@ -274,6 +274,8 @@ def run_ours(args):
     totals = torch.zeros(max(args.steps, warmup), dtype=torch.int64, device=dev)
     if args.park is not None:
         kw["park_after"] = args.park
+    if args.ctas_per_sm is not None:
+        kw["ctas_per_sm"] = args.ctas_per_sm
 
     def resident_steps(n_steps, first):
         for k in range(n_steps):
@@ -294,6 +296,7 @@ def run_ours(args):
     ev[0].record()
     resident_steps(args.steps, 3)
     ev[1].record()
+    host_enqueue_ms = (time.perf_counter() - win_a0) * 1e3 / args.steps      # host time to queue one step
     barrier()
     win_a1 = time.perf_counter()
     ms_total = ev[0].elapsed_time(ev[1])
@@ -459,6 +462,7 @@ def run_ours(args):
                    "solver": args.solver, "pipeline_depth": args.depth,
                    "l2": "8 different stacks cycled (168 MB > 126 MB L2): inputs larger than L2", "parallelism": "field-sharded x%d, no collective" % world},
         "frames_per_s": frames_per_s, "serial_ms_per_step": serial_ms_per_step,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": d2h // max(args.steps, 1), "frames_per_s": world * args.steps * N_FRAMES / (e2e_ms * 1e-3),
                 "api": "engine.FieldStream submit/begin_fetch/end_fetch over fsq_detect / fsq_fit_candidates (pinned host frames in, packed results out)"},
@@ -485,6 +489,7 @@ def main():
     ap.add_argument("--depth", type=int, default=3, help="batches in flight (streams) in the pipelined regions")
     ap.add_argument("--no-parity-solver", action="store_true")
     ap.add_argument("--park", type=int, default=None, help="fsq_lm_opts.park_after override (scheduling only)")
+    ap.add_argument("--ctas-per-sm", type=int, default=None, help="fsq_lm_opts.ctas_per_sm override (scheduling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -683,7 +683,8 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel, WTHREADS, 0) != cudaSuccess || v < 1) v = 2;
         per_sm = v;
     }
-    long long blocks = (long long)sm_count() * per_sm;
+    const int use_per_sm = (opts->ctas_per_sm > 0 && opts->ctas_per_sm < per_sm) ? opts->ctas_per_sm : per_sm;
+    long long blocks = (long long)sm_count() * use_per_sm;
     const long long need = (n + WTHREADS - 1) / WTHREADS;
     if (need < blocks) blocks = need < 1 ? 1 : need;
     // phase 1: every fit, parked after `cap` passes; phase 2: the parked fits to the end

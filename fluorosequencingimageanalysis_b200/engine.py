@@ -330,7 +330,7 @@ class FieldPipeline(object):
 
     def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
                  median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
-                 device=None, solver="fast", park_after=None):
+                 device=None, solver="fast", park_after=None, ctas_per_sm=None):
         require_cuda()
         self.L = _lib.load()
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -342,7 +342,7 @@ class FieldPipeline(object):
         self.K = _check_kernel(correlation_matrix)
         self.mf = int(median_filter_size)
         self.c_std = float(c_std)
-        self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after)
+        self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after, ctas_per_sm=ctas_per_sm)
         self.solver = solver
         if cap_per_frame is None:
             cap_per_frame = max(1024, int(0.06 * H * W))

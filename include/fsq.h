@@ -101,7 +101,10 @@ typedef struct fsq_lm_opts {
                            finished by a second launch over the parked fits, so that a handful of
                            100+-iteration fits do not pin whole thread blocks.  0 = one launch
                            (default; on B200 the two-launch schedule measured no faster).   */
-    int32_t reserved;
+    int32_t ctas_per_sm;/* FAST solver scheduling only: thread blocks per SM of the persistent LM launch.
+                           0 = as many as fit (3).  1 leaves two thirds of every SM to launches queued on
+                           other streams: with several batches in flight (engine.FieldStream) each
+                           batch's long-fit tail then runs underneath the other batches' bulk.    */
 } fsq_lm_opts;
 
 /* Solvers behind the two fit entry points.

@@ -96,7 +96,7 @@ def tri_solve(L, okc, rhs):
     return y
 
 
-def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fdt=None, maxiter=200,
+def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fdt=None, maxiter=200, tr='lm',
              ftol=1e-10, xtol=1e-10, gtol=1e-10, factor=100.0, rank_eps=None, verbose=False):
     """data [N,win,win]; returns dict(params, status, niter, nfev, chi2)."""
     N, win, _ = data.shape
@@ -180,6 +180,33 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fd
         fp = dxn - dl
         pr = np.zeros(len(idx))
         todo = fp > 0.1 * dl
+        dog = np.zeros(len(idx), dtype=bool)
+        if tr == 'dogleg' and todo.any():
+            # Powell dogleg in the scaled variables y = S p, trust region |W y| <= delta, W^2 = T
+            Wd2 = 1.0 / T                                        # W^-2
+            sdir = -Wd2 * gs                                        # steepest descent in the W metric
+            Cd = np.einsum("nkl,nl->nk", C, sdir)
+            dCd = (sdir * Cd).sum(axis=1)
+            gWg = (gs * Wd2 * gs).sum(axis=1)
+            tau = gWg / np.where(dCd > 0, dCd, 1)
+            yc = tau[:, None] * sdir
+            nyc = np.sqrt((T * yc * yc).sum(axis=1))
+            nd = np.sqrt((T * sdir * sdir).sum(axis=1))
+            ygn = y
+            v = ygn - yc
+            a_ = (T * v * v).sum(axis=1)
+            b_ = 2 * (T * yc * v).sum(axis=1)
+            c_ = nyc ** 2 - dl ** 2
+            disc = np.maximum(b_ * b_ - 4 * a_ * c_, 0)
+            beta = (-b_ + np.sqrt(disc)) / np.where(a_ > 0, 2 * a_, 1)
+            beta = np.clip(beta, 0, 1)
+            ydl = np.where((nyc >= dl)[:, None], (dl / np.where(nd > 0, nd, 1))[:, None] * sdir, yc + beta[:, None] * v)
+            ydl = np.where((dCd > 0)[:, None], ydl, (dl / np.where(nd > 0, nd, 1))[:, None] * sdir)
+            y = np.where(todo[:, None], ydl, y)
+            p = y / S
+            dog = todo.copy()
+            pr = np.where(todo, 1.0, 0.0)
+            todo = np.zeros_like(todo)
         if todo.any():
             full = okc.all(axis=1)
             # parl (only when full rank): phi(0)/ -phi'(0)
@@ -250,6 +277,10 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fd
         t2sq = alpha * pr * pnorm ** 2 / fn ** 2
         prered = t1sq + 2 * t2sq
         dirder = -(t1sq + t2sq)
+        if tr == 'dogleg':
+            gp = (gi * p).sum(axis=1)
+            prered = np.where(dog, -(2 * gp + pAp) / fn ** 2, prered)
+            dirder = np.where(dog, gp / fn ** 2, dirder)
         with np.errstate(divide="ignore", invalid="ignore"):
             ratio = np.where(prered != 0, actred / prered, 0.0)
         low = ratio <= 0.25
@@ -290,6 +321,7 @@ def main():
     ap.add_argument("--ftol", type=float, default=1e-10)
     ap.add_argument("--xtol", type=float, default=1e-10)
     ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--tr", default="lm")
     a = ap.parse_args()
     from fluorosequencingimageanalysis_b200 import synth, pflib
     from oracle.stability import agree
@@ -305,7 +337,7 @@ def main():
     acc = {"f32": np.float32, "f64": np.float64}[a.acc]
     t = time.time()
     fdt = {"f32": np.float32, "f64": np.float64, "": None}[a.fdt]
-    r = fast_fit(subs, p0, lo, hi, ll, lh, dt=dt, acc=acc, fdt=fdt, ftol=a.ftol, xtol=a.xtol)
+    r = fast_fit(subs, p0, lo, hi, ll, lh, dt=dt, acc=acc, fdt=fdt, ftol=a.ftol, xtol=a.xtol, tr=a.tr)
     print("time %.1fs" % (time.time() - t))
     P = r["params"]
     for key in ("clean", "ref"):
