@@ -954,6 +954,10 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
                         double* out_fit, int32_t* out_int, double* fit_img, void* scratch, cudaStream_t st);
 long long warp_scratch_bytes(long long n);
+int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int win, const double* p0, const double* lo,
+                        const double* hi, const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
+                        double* params, int32_t* status, int32_t* niter, int32_t* nfev, double* chi2,
+                        int32_t* n_damped, double* fit_img, cudaStream_t st);
 // fsq_lmfast.cu
 int fast_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
@@ -1011,6 +1015,12 @@ extern "C" int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n
         return FSQ_E_ARG;
     }
     if (opts->want_perror && !perror) { set_error("fsq_gaussfit_batch: want_perror set but perror is NULL"); return FSQ_E_ARG; }
+    if (opts->solver == FSQ_SOLVER_FAST) {
+        if (win != 5 && win != 11) { set_error("fsq_gaussfit_batch: FSQ_SOLVER_FAST takes 5x5 or 11x11 windows (got %d); use FSQ_SOLVER_MINPACK", win); return FSQ_E_ARG; }
+        if (opts->want_perror) { set_error("fsq_gaussfit_batch: want_perror needs FSQ_SOLVER_MINPACK"); return FSQ_E_ARG; }
+        return warp_gaussfit_batch(windows, dtype_code, n, win, p0, lo, hi, lim_lo, lim_hi, opts, params, status, niter, nfev,
+                                   chi2, n_qrsolv, fit_img, (cudaStream_t)stream);
+    }
     if (opts->solver != FSQ_SOLVER_MINPACK) {
         if (win != 5) { set_error("fsq_gaussfit_batch: the FAST solvers take 5x5 windows (got %d); use FSQ_SOLVER_MINPACK", win); return FSQ_E_ARG; }
         if (opts->want_perror) { set_error("fsq_gaussfit_batch: want_perror needs FSQ_SOLVER_MINPACK"); return FSQ_E_ARG; }

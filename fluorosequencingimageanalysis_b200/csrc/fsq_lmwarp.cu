@@ -52,6 +52,10 @@ __host__ __device__ constexpr int wtri(int i, int j) { return i * (i + 1) / 2 + 
 struct WarpArgs {
     const void* frames; int fdtype; int H; int W;
     const int32_t* cand_hw; const int32_t* cand_frame;
+    // generic-window entry (fsq_gaussfit_batch): windows + per-fit start / limits in, mpfit fields out
+    const void* windows; int wdtype;
+    const double* p0; const double* lo; const double* hi; const uint8_t* lim_lo; const uint8_t* lim_hi;
+    double* params; int32_t* status; int32_t* niter; int32_t* nfev; double* chi2; int32_t* n_damped;
     long long n; const long long* n_dev;
     fsq_lm_opts o;
     double* out_fit; int32_t* out_int; double* fit_img;
@@ -84,12 +88,34 @@ __device__ __forceinline__ int w_ld_int(const void* base, int dtype, size_t off)
     }
 }
 
+__device__ __forceinline__ double w_ld_dbl(const void* base, int dtype, size_t off) {
+    switch (dtype) {
+        case FSQ_U8:  return (double)((const uint8_t*)base)[off];
+        case FSQ_U16: return (double)((const uint16_t*)base)[off];
+        case FSQ_I16: return (double)((const int16_t*)base)[off];
+        case FSQ_I32: return (double)((const int32_t*)base)[off];
+        case FSQ_I64: return (double)((const long long*)base)[off];
+        default:      return ((const double*)base)[off];
+    }
+}
+
 // pflib limits (pflib.py:199-213): lower on all seven, upper on centres, widths, angle
 __device__ __forceinline__ double pf_lo(int j, double lo1) {
     return j == 0 ? 0.0 : j == 1 ? lo1 : (j == 2 || j == 3) ? 2.0 : (j == 4 || j == 5) ? 0.75 : 0.0;
 }
 __device__ __forceinline__ double pf_hi(int j) { return (j == 2 || j == 3) ? 3.0 : (j == 4 || j == 5) ? 2.0 : 360.0; }
 constexpr unsigned PF_QLL = 0x7fu, PF_QUL = 0x7cu;
+
+// Box limits of one fit: compile-time constants on the pflib path (only the amplitude floor varies),
+// per-fit arrays in global memory on the generic path (read where needed: twice per tick).
+template <bool PFLIB>
+struct Lim {
+    double lo1; const double* lo; const double* hi; unsigned qll, qul;
+    __device__ __forceinline__ bool has_lo(int j) const { return PFLIB ? true : ((qll >> j) & 1u); }
+    __device__ __forceinline__ bool has_hi(int j) const { return PFLIB ? ((PF_QUL >> j) & 1u) : ((qul >> j) & 1u); }
+    __device__ __forceinline__ double lower(int j) const { return PFLIB ? pf_lo(j, lo1) : lo[j]; }
+    __device__ __forceinline__ double upper(int j) const { return PFLIB ? pf_hi(j) : hi[j]; }
+};
 
 // -------------------------------------------------------------------------------------------
 // Start values + fit-independent metrics, one thread per candidate.
@@ -138,7 +164,9 @@ fit_prep_kernel(const WarpArgs a) {
 // polynomial (|r| <= ln2/2: 2 ulp, measured against numpy.exp), argument <= 0 and bounded by the
 // pflib limits (widths >= 0.75, centres in [2,3] => |arg| < 64), so no range checks.
 // -------------------------------------------------------------------------------------------
+template <bool CLAMP>
 __device__ __forceinline__ double w_exp_neg(double u) {
+    if (CLAMP) u = fmax(u, -700.0);              // generic windows: widths / offsets are not bounded
     const double kf = fma(u, 1.4426950408889634, 6755399441055744.0);        // round(u / ln2) in the low word
     const int k = __double2loint(kf);
     const double kd = kf - 6755399441055744.0;
@@ -194,12 +222,13 @@ __device__ __forceinline__ void w_sincos_deg(double th, double* sn, double* cs) 
 //     M = As + par * T,   As = S^-1 A S^-1 (unit diagonal),  T = (D/S)^2
 // As read from shared memory ([entry][thread]); singular pivots are skipped (Li = 0).
 // -------------------------------------------------------------------------------------------
+template <int TPB>
 __device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const float (&T)[WNP],
                                             float par, float (&L)[WNT], float (&Li)[WNP], float eps) {
     unsigned ok = 0;
 #pragma unroll
     for (int j = 0; j < WNP; ++j) {
-        float dj = fmaf(par, T[j], sA[wtri(j, j) * WTHREADS]);
+        float dj = fmaf(par, T[j], sA[wtri(j, j) * TPB]);
 #pragma unroll
         for (int k = 0; k < j; ++k) dj = fmaf(-L[wtri(j, k)], L[wtri(j, k)], dj);
         const bool good = dj > eps;
@@ -209,7 +238,7 @@ __device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const 
         ok |= (good ? 1u : 0u) << j;
 #pragma unroll
         for (int i = j + 1; i < WNP; ++i) {
-            float sacc = sA[wtri(i, j) * WTHREADS];
+            float sacc = sA[wtri(i, j) * TPB];
 #pragma unroll
             for (int k = 0; k < j; ++k) sacc = fmaf(-L[wtri(i, k)], L[wtri(j, k)], sacc);
             L[wtri(i, j)] = sacc * inv;
@@ -239,6 +268,7 @@ __device__ __forceinline__ void w_bwd7(const float (&L)[WNT], const float (&Li)[
 }
 
 // One pass over the window at pt: chi^2 in FP64; J^T J (packed), J^T f in FP32 (J = d residual / dp).
+template <int WIN, int TPB, bool CLAMP>
 __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __restrict__ sd,
                                        float (&A)[WNT], float (&g)[WNP], double& ss_out) {
     const double Hh = pt[0], Aa = pt[1];
@@ -246,17 +276,23 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     w_sincos_deg(pt[6], &sn, &cs);                                            // gaussfitter.py:115
     const double iwx = 1.0 / pt[4], iwy = 1.0 / pt[5];
     const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
-    double ca[5], cb[5];
-    float caf[5], cbf[5];
+    // per-column terms of the rotated offsets (numpy.indices: y = column index pairs with p[2]);
+    // 5x5: tables in registers; larger windows: one multiply-add per pixel instead
+    constexpr bool TABLES = (WIN <= 5);
+    double ca[TABLES ? WIN : 1], cb[TABLES ? WIN : 1];
+    float caf[TABLES ? WIN : 1], cbf[TABLES ? WIN : 1];
+    if (TABLES) {
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const double dy = pt[2] - (double)c;            // numpy.indices: y = column index pairs with p[2]
-        ca[c] = dy * sxs; cb[c] = dy * cys;
-        caf[c] = (float)ca[c]; cbf[c] = (float)cb[c];
+        for (int c = 0; c < (TABLES ? WIN : 1); ++c) {
+            const double dy = pt[2] - (double)c;
+            ca[c] = dy * sxs; cb[c] = dy * cys;
+            caf[c] = (float)ca[c]; cbf[c] = (float)cb[c];
+        }
     }
     const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
     const float iwxf = (float)iwx, iwyf = (float)iwy;
     const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
+    const float cyf = (float)pt[2];
 #pragma unroll
     for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
 #pragma unroll
@@ -264,18 +300,27 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     double ss = 0.0;
     double dx = pt[3];                                  // x = row index pairs with p[3]
 #pragma unroll 1
-    for (int r = 0; r < 5; ++r) {
+    for (int r = 0; r < WIN; ++r) {
         const double ra = dx * cxs, rb = dx * sys;
         const float raf = (float)ra, rbf = (float)rb;
-        const double* drow = sd + r * 5 * WTHREADS;
+        const double* drow = sd + r * WIN * TPB;
         dx -= 1.0;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const double av = ra - ca[c], bv = rb + cb[c];
-            const double E = w_exp_neg(-0.5 * fma(bv, bv, av * av));
-            const double f = drow[c * WTHREADS] - fma(Aa, E, Hh);
+        for (int c = 0; c < WIN; ++c) {
+            double av, bv;
+            float af, bf;
+            if (TABLES) {
+                av = ra - ca[c]; bv = rb + cb[c];
+                af = raf - caf[c]; bf = rbf + cbf[c];
+            } else {
+                const double dy = pt[2] - (double)c;
+                const float dyf = cyf - (float)c;
+                av = fma(-dy, sxs, ra); bv = fma(dy, cys, rb);
+                af = fmaf(-dyf, sx, raf); bf = fmaf(dyf, cyw, rbf);
+            }
+            const double E = w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
+            const double f = drow[c * TPB] - fma(Aa, E, Hh);
             ss = fma(f, f, ss);
-            const float af = raf - caf[c], bf = rbf + cbf[c];
             const float Ef = (float)E, ff = (float)f;
             const float AE = Af * Ef;
             const float AEa = AE * af, AEb = AE * bf;
@@ -297,7 +342,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
             }
         }
     }
-    A[0] = 25.0f;
+    A[0] = (float)(WIN * WIN);
     ss_out = ss;
 }
 
@@ -307,11 +352,14 @@ enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
 #define WLMPAR_MAX 10      // lmpar iteration limit (mpfit.py:2148)
 #endif
 
-__global__ void __launch_bounds__(WTHREADS, WMINB)
+template <int WIN, int TPB, int MINB, bool PFLIB>
+__global__ void __launch_bounds__(TPB, MINB)
 lmwarp_kernel(const WarpArgs a) {
-    __shared__ double s_d[25 * WTHREADS];
-    __shared__ float s_A[WNT * WTHREADS];      // column-scaled J^T J at the current point
-    __shared__ float s_g[WNP * WTHREADS];      // column-scaled J^T f
+    constexpr int P = WIN * WIN;
+    extern __shared__ __align__(16) unsigned char w_smem[];
+    double* const s_d = reinterpret_cast<double*>(w_smem);                 // [P][TPB] pixels
+    float* const s_A = reinterpret_cast<float*>(s_d + P * TPB);            // [28][TPB] column-scaled J^T J at the current point
+    float* const s_g = s_A + WNT * TPB;                                    // [7][TPB]  column-scaled J^T f
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     double* const sd = s_d + tid;
@@ -333,7 +381,9 @@ lmwarp_kernel(const WarpArgs a) {
     unsigned lpeg = 0, upeg = 0;
     bool nonfinite = false;
     double x[WNP], y[WNP];
-    double lo1 = 0.0, ss0 = -1.0, ss1 = -1.0;           // chi^2 at x, chi^2 of the last trial point
+    double ss0 = -1.0, ss1 = -1.0;                      // chi^2 at x, chi^2 of the last trial point
+    Lim<PFLIB> lim;
+    lim.lo1 = 0.0; lim.lo = nullptr; lim.hi = nullptr; lim.qll = PF_QLL; lim.qul = PF_QUL;
     float delta = 0.0f, par = 0.0f, xnorm = 0.0f, gnorm = 0.0f, pnorm = 0.0f, prered = 0.0f, dirder = 0.0f, rss0 = 0.0f;
     float diag[WNP], iS[WNP];
 #pragma unroll
@@ -353,25 +403,54 @@ lmwarp_kernel(const WarpArgs a) {
                 if (slot >= n_total) exhausted = true;
                 else {
                     idx = a.resume ? a.strag[slot].idx : slot;
-                    cand_h = a.cand_hw[2 * idx]; cand_w = a.cand_hw[2 * idx + 1];
-                    const size_t fbase = (size_t)a.cand_frame[idx] * a.H * a.W + (size_t)(cand_h - 2) * a.W + (cand_w - 2);
+                    if (PFLIB) {
+                        cand_h = a.cand_hw[2 * idx]; cand_w = a.cand_hw[2 * idx + 1];
+                        const size_t fbase = (size_t)a.cand_frame[idx] * a.H * a.W + (size_t)(cand_h - 2) * a.W + (cand_w - 2);
 #pragma unroll 1
-                    for (int r = 0; r < 5; ++r)
+                        for (int r = 0; r < WIN; ++r)
 #pragma unroll
-                        for (int c = 0; c < 5; ++c)
-                            sd[(r * 5 + c) * WTHREADS] = (double)w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
-                    const int4 pre = *reinterpret_cast<const int4*>(a.out_int + idx * 4);
-                    const double dmax = (double)pre.y, dmean = (double)pre.z / 25.0;
-                    lo1 = (dmax - dmean) / 3.0;                                        // pflib.py:205
-                    x[0] = (double)pre.x; x[1] = dmax; x[2] = 2.5; x[3] = 2.5; x[4] = 1.0; x[5] = 1.0; x[6] = 0.0;
+                            for (int c = 0; c < WIN; ++c)
+                                sd[(r * WIN + c) * TPB] = (double)w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
+                        const int4 pre = *reinterpret_cast<const int4*>(a.out_int + idx * 4);
+                        const double dmax = (double)pre.y, dmean = (double)pre.z / 25.0;
+                        lim.lo1 = (dmax - dmean) / 3.0;                                    // pflib.py:205
+                        x[0] = (double)pre.x; x[1] = dmax; x[2] = 2.5; x[3] = 2.5; x[4] = 1.0; x[5] = 1.0; x[6] = 0.0;
 #pragma unroll
-                    for (int j = 0; j < WNP; ++j) {                                    // gaussfitter.py:202-204
-                        if (((PF_QUL >> j) & 1u) && x[j] > pf_hi(j)) x[j] = pf_hi(j);
-                        if (x[j] < pf_lo(j, lo1)) x[j] = pf_lo(j, lo1);
-                        y[j] = x[j];
+                        for (int j = 0; j < WNP; ++j) {                                    // gaussfitter.py:202-204
+                            if (lim.has_hi(j) && x[j] > lim.upper(j)) x[j] = lim.upper(j);
+                            if (x[j] < lim.lower(j)) x[j] = lim.lower(j);
+                            y[j] = x[j];
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int q = 0; q < P; ++q) sd[q * TPB] = w_ld_dbl(a.windows, a.wdtype, (size_t)idx * P + q);
+                        lim.lo = a.lo + idx * WNP; lim.hi = a.hi + idx * WNP;
+                        lim.qll = 0; lim.qul = 0;
+#pragma unroll
+                        for (int j = 0; j < WNP; ++j) {
+                            x[j] = a.p0[idx * WNP + j]; y[j] = x[j];
+                            lim.qll |= (a.lim_lo[idx * WNP + j] ? 1u : 0u) << j;
+                            lim.qul |= (a.lim_hi[idx * WNP + j] ? 1u : 0u) << j;
+                        }
                     }
                     active = true; mode = MODE_FIRST; status = 0; niter = 1; nfev = 0; n_damped = 0;
                     ss0 = -1.0; ss1 = -1.0; par = 0.0f; nonfinite = false;
+                    if (!PFLIB) {
+                        // mpfit.py:956-964: start outside the limits / inconsistent limits -> status 0, nothing runs
+                        bool bad = false;
+#pragma unroll
+                        for (int j = 0; j < WNP; ++j) {
+                            const bool ql = lim.has_lo(j), qu = lim.has_hi(j);
+                            bad |= (ql && x[j] < lim.lower(j)) || (qu && x[j] > lim.upper(j)) || (ql && qu && lim.lower(j) >= lim.upper(j));
+                        }
+                        if (bad) {
+#pragma unroll
+                            for (int j = 0; j < WNP; ++j) a.params[idx * WNP + j] = x[j];
+                            a.status[idx] = 0; a.niter[idx] = 0; a.nfev[idx] = 0; a.chi2[idx] = -1.0;
+                            if (a.n_damped) a.n_damped[idx] = 0;
+                            active = false;
+                        }
+                    }
                     if (a.resume) {
                         const StragRec* rec = a.strag + slot;
 #pragma unroll
@@ -383,13 +462,16 @@ lmwarp_kernel(const WarpArgs a) {
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;      // queue drained and nothing running
+            continue;                                                    // (a refill can end at once: status 0)
+        }
 
         if (active) {
             // -------------------------------------------------------------- pass at the trial point
             float An[WNT], gn[WNP];
             double ss;
-            w_pass(y, sd, An, gn, ss);                      // y == x on the first tick of a fit
+            w_pass<WIN, TPB, !PFLIB>(y, sd, An, gn, ss);                      // y == x on the first tick of a fit
             if (mode != MODE_RESUME) ++nfev;
 
             bool have_new = false;
@@ -458,8 +540,8 @@ lmwarp_kernel(const WarpArgs a) {
                 lpeg = 0; upeg = 0;
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) {
-                    const bool lp = (x[j] == pf_lo(j, lo1));
-                    const bool up = ((PF_QUL >> j) & 1u) && (x[j] == pf_hi(j));
+                    const bool lp = lim.has_lo(j) && (x[j] == lim.lower(j));
+                    const bool up = lim.has_hi(j) && (x[j] == lim.upper(j));
                     lpeg |= (lp ? 1u : 0u) << j; upeg |= (up ? 1u : 0u) << j;
                     const bool zero = (lp && gn[j] > 0.0f) || (up && gn[j] < 0.0f);
                     const float keep = zero ? 0.0f : 1.0f;
@@ -498,8 +580,8 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
                 for (int i = 0; i < WNP; ++i) {
 #pragma unroll
-                    for (int k = 0; k <= i; ++k) sA[wtri(i, k) * WTHREADS] = An[wtri(i, k)] * (iS[i] * iS[k]);
-                    sg[i * WTHREADS] = gn[i];
+                    for (int k = 0; k <= i; ++k) sA[wtri(i, k) * TPB] = An[wtri(i, k)] * (iS[i] * iS[k]);
+                    sg[i * TPB] = gn[i];
                 }
             }
 
@@ -509,12 +591,12 @@ lmwarp_kernel(const WarpArgs a) {
                 // ---------------------------------------------------------- lmpar (:2077-2190), FP32
                 float L[WNT], Li[WNP], rhs[WNP], z[WNP], T[WNP], pf[WNP];
 #pragma unroll
-                for (int i = 0; i < WNP; ++i) { rhs[i] = -sg[i * WTHREADS]; const float t = diag[i] * iS[i]; T[i] = t * t; }
+                for (int i = 0; i < WNP; ++i) { rhs[i] = -sg[i * TPB]; const float t = diag[i] * iS[i]; T[i] = t * t; }
                 float prr = 0.0f, par_used = 0.0f, fp = 0.0f, parl = 0.0f, paru = 0.0f, dxnorm = 0.0f;
                 unsigned ok = 0;
 #pragma unroll 1
                 for (int it = 0; it <= WLMPAR_MAX; ++it) {
-                    const unsigned okk = w_chol7(sA, T, prr, L, Li, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f);
+                    const unsigned okk = w_chol7<TPB>(sA, T, prr, L, Li, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f);
                     if (it == 0) ok = okk;
                     w_fwd7(L, Li, rhs, z);
                     w_bwd7(L, Li, z);
@@ -578,8 +660,8 @@ lmwarp_kernel(const WarpArgs a) {
                 for (int j = 0; j < WNP; ++j) {
                     const double xn = x[j] + (double)pf[j];
                     if (fabsf(pf[j]) > machep) {
-                        if (xn < pf_lo(j, lo1)) alpha = fminf(alpha, __fdividef((float)(pf_lo(j, lo1) - x[j]), pf[j]) * (1.0f + 4e-7f));
-                        if (((PF_QUL >> j) & 1u) && (xn > pf_hi(j))) alpha = fminf(alpha, __fdividef((float)(pf_hi(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (lim.has_lo(j) && xn < lim.lower(j)) alpha = fminf(alpha, __fdividef((float)(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (lim.has_hi(j) && xn > lim.upper(j)) alpha = fminf(alpha, __fdividef((float)(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
                     }
                 }
                 float pn = 0.0f;
@@ -588,13 +670,26 @@ lmwarp_kernel(const WarpArgs a) {
                 for (int j = 0; j < WNP; ++j) {
                     pf[j] *= alpha;
                     double xn = x[j] + (double)pf[j];
-                    const double ll = pf_lo(j, lo1);
-                    const double llim1 = ll * (1.0 + WQ_MACHEP) + ((ll == 0.0) ? WQ_MACHEP : 0.0);   // ll >= 0 here
-                    if ((PF_QUL >> j) & 1u) {
-                        const double ul = pf_hi(j);
-                        if (xn >= ul * (1.0 - WQ_MACHEP)) xn = ul;
+                    if (PFLIB) {
+                        const double ll = lim.lower(j);
+                        const double llim1 = ll * (1.0 + WQ_MACHEP) + ((ll == 0.0) ? WQ_MACHEP : 0.0);   // ll >= 0 here
+                        if (lim.has_hi(j)) {
+                            const double ul = lim.upper(j);
+                            if (xn >= ul * (1.0 - WQ_MACHEP)) xn = ul;
+                        }
+                        if (xn <= llim1) xn = ll;
+                    } else {                                                             // :1220-1231, any sign
+                        if (lim.has_hi(j)) {
+                            const double ul = lim.upper(j);
+                            const double sgnu = (ul >= 0.0) ? 1.0 : -1.0;
+                            if (xn >= ul * (1.0 - sgnu * WQ_MACHEP) - ((ul == 0.0) ? WQ_MACHEP : 0.0)) xn = ul;
+                        }
+                        if (lim.has_lo(j)) {
+                            const double ll = lim.lower(j);
+                            const double sgnl = (ll >= 0.0) ? 1.0 : -1.0;
+                            if (xn <= ll * (1.0 + sgnl * WQ_MACHEP) + ((ll == 0.0) ? WQ_MACHEP : 0.0)) xn = ll;
+                        }
                     }
-                    if (xn <= llim1) xn = ll;
                     y[j] = xn;
                     const float t = diag[j] * pf[j];
                     pn = fmaf(t, t, pn);
@@ -611,7 +706,7 @@ lmwarp_kernel(const WarpArgs a) {
                     for (int i = 0; i < WNP; ++i) {
                         float s = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < WNP; ++j) s = fmaf(sA[((i >= j) ? wtri(i, j) : wtri(j, i)) * WTHREADS], zs[j], s);
+                        for (int j = 0; j < WNP; ++j) s = fmaf(sA[((i >= j) ? wtri(i, j) : wtri(j, i)) * TPB], zs[j], s);
                         pAp = fmaf(s, zs[i], pAp);
                     }
                 }
@@ -624,15 +719,23 @@ lmwarp_kernel(const WarpArgs a) {
             } else {
                 // ---------------------------------------------------------- results (pflib.py:461-477)
                 if (status > 0) ++nfev;                                                  // :1351-1355
-                double* o = a.out_fit + idx * 12;
-                const double sst = o[8];
-                o[0] = (x[2] + (double)cand_h) - 2.5;                                    // pflib.py:461
-                o[1] = (x[3] + (double)cand_w) - 2.5;
-                o[2] = x[0]; o[3] = x[1]; o[4] = x[4]; o[5] = x[5]; o[6] = x[6];
-                o[7] = sqrt(ss0 / 25.0); o[8] = 1.0 - ss0 / sst;   // ss0 = residual sum of squares at the final parameters
-                o[10] = fmax(ss0, ss1);                                                  // mpfit .fnorm (:1357-1359)
-                o[11] = sqrt(ss0);
-                *reinterpret_cast<int4*>(a.out_int + idx * 4) = make_int4(status, niter, nfev, n_damped);
+                if (PFLIB) {
+                    double* o = a.out_fit + idx * 12;
+                    const double sst = o[8];
+                    o[0] = (x[2] + (double)cand_h) - 2.5;                                // pflib.py:461
+                    o[1] = (x[3] + (double)cand_w) - 2.5;
+                    o[2] = x[0]; o[3] = x[1]; o[4] = x[4]; o[5] = x[5]; o[6] = x[6];
+                    o[7] = sqrt(ss0 / 25.0); o[8] = 1.0 - ss0 / sst;   // ss0 = residual sum of squares at the final parameters
+                    o[10] = fmax(ss0, ss1);                                              // mpfit .fnorm (:1357-1359)
+                    o[11] = sqrt(ss0);
+                    *reinterpret_cast<int4*>(a.out_int + idx * 4) = make_int4(status, niter, nfev, n_damped);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < WNP; ++j) a.params[idx * WNP + j] = x[j];
+                    a.status[idx] = status; a.niter[idx] = niter; a.nfev[idx] = nfev;
+                    a.chi2[idx] = fmax(ss0, ss1);
+                    if (a.n_damped) a.n_damped[idx] = n_damped;
+                }
                 active = false;
             }
         }
@@ -662,7 +765,59 @@ fit_image_kernel(const WarpArgs a) {
     }
 }
 
+// same for the generic entry: params [n,7] -> fit_img [n,win,win]
+__global__ void __launch_bounds__(128)
+fit_image_generic_kernel(const double* __restrict__ params, const int32_t* __restrict__ status, long long n, int win,
+                         double* __restrict__ fit_img) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* o = params + i * 7;
+    double sn, cs;
+    sincos(WQ_DEG2RAD * o[6], &sn, &cs);
+    const double iwx = 1.0 / o[4], iwy = 1.0 / o[5];
+    for (int r = 0; r < win; ++r) {
+        const double dx = o[3] - (double)r;
+        for (int c = 0; c < win; ++c) {
+            const double dy = o[2] - (double)c;
+            const double aa = (dx * cs - dy * sn) * iwx;
+            const double bb = (dx * sn + dy * cs) * iwy;
+            fit_img[(i * win + r) * win + c] = o[0] + o[1] * exp(-0.5 * (aa * aa + bb * bb));
+        }
+    }
+}
+
 long long warp_scratch_bytes(long long n) { return 64 + (long long)sizeof(StragRec) * (n > 0 ? n : 0); }
+
+// Persistent launch(es) of one kernel flavour: phase 1 over every fit (parked after `park_after`
+// passes when that is set), phase 2 over the parked fits.
+template <int WIN, int TPB, int MINB, bool PFLIB>
+static int launch_warp(WarpArgs& a, const fsq_lm_opts* opts, unsigned long long* head, cudaStream_t st) {
+    constexpr size_t smem = (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB>, TPB, smem) != cudaSuccess || v < 1) v = 1;
+        per_sm = v;
+    }
+    const int use_per_sm = (opts->ctas_per_sm > 0 && opts->ctas_per_sm < per_sm) ? opts->ctas_per_sm : per_sm;
+    long long blocks = (long long)sm_count() * use_per_sm;
+    const long long need = (a.n + TPB - 1) / TPB;
+    if (need < blocks) blocks = need < 1 ? 1 : need;
+    a.cap = opts->park_after > 0 ? opts->park_after : 0; a.resume = 0;
+    lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks, TPB, smem, st>>>(a);
+    FSQ_LAUNCH_CHECK();
+    if (a.cap > 0) {
+        FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
+        a.cap = 0; a.resume = 1;
+        // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
+        // whatever the caller has queued on other streams (the next batch's detection and phase 1)
+        const long long blocks2 = blocks < sm_count() ? blocks : sm_count();
+        lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks2, TPB, smem, st>>>(a);
+        FSQ_LAUNCH_CHECK();
+    }
+    return FSQ_OK;
+}
 
 int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
                         const int32_t* cand_frame, long long n, const long long* n_dev, const fsq_lm_opts* opts,
@@ -677,31 +832,42 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     fit_prep_kernel<<<flat, 128, 0, st>>>(a);
     FSQ_LAUNCH_CHECK();
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel, WTHREADS, 0) != cudaSuccess || v < 1) v = 2;
-        per_sm = v;
-    }
-    const int use_per_sm = (opts->ctas_per_sm > 0 && opts->ctas_per_sm < per_sm) ? opts->ctas_per_sm : per_sm;
-    long long blocks = (long long)sm_count() * use_per_sm;
-    const long long need = (n + WTHREADS - 1) / WTHREADS;
-    if (need < blocks) blocks = need < 1 ? 1 : need;
-    // phase 1: every fit, parked after `cap` passes; phase 2: the parked fits to the end
-    a.cap = opts->park_after > 0 ? opts->park_after : 0; a.resume = 0;
-    lmwarp_kernel<<<(unsigned)blocks, WTHREADS, 0, st>>>(a);
-    FSQ_LAUNCH_CHECK();
-    if (a.cap > 0) {
-        FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
-        a.cap = 0; a.resume = 1;
-        // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
-        // whatever the caller has queued on other streams (the next batch's detection and phase 1)
-        const long long blocks2 = blocks < sm_count() ? blocks : sm_count();
-        lmwarp_kernel<<<(unsigned)blocks2, WTHREADS, 0, st>>>(a);
-        FSQ_LAUNCH_CHECK();
-    }
+    const int rc = launch_warp<5, WTHREADS, WMINB, true>(a, opts, head, st);
+    if (rc != FSQ_OK) return rc;
     if (fit_img) {
         fit_image_kernel<<<flat, 128, 0, st>>>(a);
+        FSQ_LAUNCH_CHECK();
+    }
+    return FSQ_OK;
+}
+
+// generic windows (fsq_gaussfit_batch with FSQ_SOLVER_FAST): win = 5 or 11, per-fit start / limits
+int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int win, const double* p0, const double* lo,
+                        const double* hi, const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
+                        double* params, int32_t* status, int32_t* niter, int32_t* nfev, double* chi2,
+                        int32_t* n_damped, double* fit_img, cudaStream_t st) {
+    WarpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.windows = windows; a.wdtype = dtype_code; a.p0 = p0; a.lo = lo; a.hi = hi; a.lim_lo = lim_lo; a.lim_hi = lim_hi;
+    a.n = n; a.o = *opts; a.params = params; a.status = status; a.niter = niter; a.nfev = nfev; a.chi2 = chi2;
+    a.n_damped = n_damped;
+    // this entry has no caller-provided scratch: a stream-ordered allocation holds the queue head and,
+    // when parking is requested, the parked states
+    fsq_lm_opts o = *opts;
+    void* scratch = nullptr;
+    const size_t bytes = (size_t)(o.park_after > 0 ? warp_scratch_bytes(n) : 64);
+    FSQ_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
+    unsigned long long* head = (unsigned long long*)scratch;
+    a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);
+    FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
+    int rc;
+    if (win == 5) rc = launch_warp<5, 128, 3, false>(a, &o, head, st);
+    else if (win == 11) rc = launch_warp<11, 64, 3, false>(a, &o, head, st);
+    else { set_error("the FAST solver takes 5x5 or 11x11 windows (got %d)", win); rc = FSQ_E_ARG; }
+    cudaFreeAsync(scratch, st);
+    if (rc != FSQ_OK) return rc;
+    if (fit_img) {
+        fit_image_generic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(params, status, n, win, fit_img);
         FSQ_LAUNCH_CHECK();
     }
     return FSQ_OK;

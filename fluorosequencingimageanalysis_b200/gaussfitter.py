@@ -135,8 +135,10 @@ def gaussfit(data, err=None, params=(), autoderiv=True, return_all=False, circle
         if params[i] < mn[i] and lmin[i]:
             params[i] = mn[i]
     win = data[None].astype(np.int64) if data.dtype.kind in "iub" else data[None].astype(np.float64)
+    # SOLVER = "fast" runs the production fitter where it applies (5x5 / 11x11 windows, no perror asked for)
+    fast_ok = SOLVER == "fast" and win.shape[1] == win.shape[2] and win.shape[1] in (5, 11) and not (return_all or returnmp)
     r = engine.gaussfit_batch(win, params[None], mn[None], mx[None], lmin[None].astype(np.uint8),
-                              lmax[None].astype(np.uint8), faithful=FAITHFUL,
+                              lmax[None].astype(np.uint8), faithful=FAITHFUL, solver="fast" if fast_ok else "minpack",
                               want_perror=bool(return_all or returnmp), want_fit_img=bool(returnfitimage))
     p = r.params[0].cpu().numpy()
     status = int(r.status[0].item())

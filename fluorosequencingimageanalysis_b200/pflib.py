@@ -77,7 +77,7 @@ def _fit_2d_gaussian(subimage, implementation='agpy'):
     sub = subimage.astype(np.int64)[None] if subimage.dtype.kind in "iub" else subimage.astype(np.float64)[None]
     p0, lo, hi, lim_lo, lim_hi = _pflib_limits(sub)
     r = engine.gaussfit_batch(sub, p0, lo, hi, lim_lo, lim_hi, faithful=FAITHFUL, want_fit_img=True,
-                              solver="minpack" if SOLVER == "minpack" else "fast64")
+                              solver=SOLVER)
     H, A, h_0, w_0, sigma_h, sigma_w, theta = (float(v) for v in r.params[0].cpu().numpy())
     return (h_0, w_0, H, A, sigma_h, sigma_w, theta, r.fit_img[0].cpu().numpy())
 

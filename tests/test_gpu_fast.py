@@ -182,3 +182,87 @@ def test_drop_in_find_peptides_with_the_fast_solver(fits5, frame0):
     assert (d <= 1.5).mean() >= 0.95
     v = next(iter(out.values()))
     assert len(v) == 12 and v[7].dtype == np.int64 and v[8].dtype == np.float64
+
+
+# ------------------------------------------------------------------------------------ generic windows
+def test_fast_generic_5x5_is_the_frame_path_bit_for_bit(fast5, fits5, frame0):
+    """fsq_gaussfit_batch(solver=FAST) on host-cut windows with host-marshalled pflib limits must
+    be the same program as fsq_fit_candidates (window gather, start values and limits on the device)."""
+    engine, pflib, _, _ = _mods()
+    cands = fits5["cands"]
+    subs = np.stack([frame0[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in cands])
+    p0, lo, hi, lim_lo, lim_hi = pflib._pflib_limits(subs)
+    r = engine.gaussfit_batch(subs, p0, lo, hi, lim_lo, lim_hi, solver="fast", want_fit_img=True)
+    P = r.params.cpu().numpy()
+    W = _window_params(fast5)
+    # H, A, widths, theta are stored untouched; centres go through the image-coordinate map of pflib.py:461
+    for col in (0, 1, 4, 5, 6):
+        assert np.array_equal(P[:, col], W[:, col])
+    assert np.abs(P[:, 2:4] - W[:, 2:4]).max() < 1e-12
+    assert np.array_equal(r.status.cpu().numpy(), fast5.ints[:, 0])
+    assert np.array_equal(r.niter.cpu().numpy(), fast5.ints[:, 1])
+    assert np.array_equal(r.chi2.cpu().numpy(), fast5.fit[:, 10])
+    i = 17
+    assert np.allclose(r.fit_img[i].cpu().numpy(), po.gauss2d(P[i], (5, 5)), rtol=1e-12)
+
+
+def test_fast_11x11_default_gaussfit_arguments():
+    """BASELINE configs[0] direct-gaussfit variant through the FAST solver: 11x11 windows, moments
+    start, default limits (gaussfitter.py:142-148)."""
+    engine, _, _, _ = _mods()
+    g = golden("fits11_seed0.npz")
+    st = golden("stable11_seed0.npz")
+    n = len(g["windows"])
+    lo = np.zeros((n, 7))
+    hi = np.tile(np.array([0, 0, 0, 0, 0, 0, 360.]), (n, 1))
+    lmin = np.tile(np.array([0, 0, 0, 0, 1, 1, 1], dtype=np.uint8), (n, 1))
+    lmax = np.tile(np.array([0, 0, 0, 0, 0, 0, 1], dtype=np.uint8), (n, 1))
+    r = engine.gaussfit_batch(g["windows"], g["p0"], lo, hi, lmin, lmax, solver="fast", want_fit_img=True)
+    P, s, chi = r.params.cpu().numpy(), r.status.cpu().numpy(), r.chi2.cpu().numpy()
+    assert (s > 0).all()
+    # same contract as 5x5: (1) the robust set of the reference (never left the Gauss-Newton branch of
+    # lmpar, stable answer); (2) at least as converged as the reference everywhere (its status-2 exits on
+    # this set are premature: chi^2 up to 30 % above the minimum); (3) the clean oracle on its stable set
+    robust = st["stable_ref"] & (g["n_qrsolv"] == 0)
+    ok_ref, ok_clean = agree(P, g["ref_params"]), agree(P, g["clean_params"])
+    nw = chi <= g["ref_fnorm"] * (1 + 1e-6)
+    print("fast 11x11: robust-set agreement %.4f (n=%d); vs clean oracle on its stable set %.4f (n=%d); "
+          "chi2 not worse than the reference %.4f" % (ok_ref[robust].mean(), robust.sum(),
+                                                      ok_clean[st["stable_clean"]].mean(), st["stable_clean"].sum(), nw.mean()))
+    assert robust.sum() > 100
+    assert ok_ref[robust].mean() >= 0.99
+    assert ok_clean[st["stable_clean"]].mean() >= 0.97
+    assert nw.mean() >= 0.98
+    i = 5
+    assert np.allclose(r.fit_img[i].cpu().numpy(), po.gauss2d(P[i], (11, 11)), rtol=1e-12)
+
+
+def test_fast_generic_edge_cases():
+    engine, _, _, _ = _mods()
+    # start outside the limits -> status 0, parameters untouched (mpfit.py:956-959); a whole warp of them
+    w = np.repeat(po.gauss2d([10, 100, 2.5, 2.5, 1, 1, 0], (5, 5))[None], 40, axis=0)
+    p0 = np.tile(np.array([[10, 100, 2.5, 2.5, 3.0, 1, 0.]]), (40, 1))
+    lo = np.tile(np.array([[0, 0, 2, 2, .75, .75, 0.]]), (40, 1))
+    hi = np.tile(np.array([[0, 0, 3, 3, 2, 2, 360.]]), (40, 1))
+    r = engine.gaussfit_batch(w, p0, lo, hi, np.ones((40, 7), np.uint8),
+                              np.tile(np.array([[0, 0, 1, 1, 1, 1, 1]], np.uint8), (40, 1)), solver="fast")
+    assert (r.status.cpu().numpy() == 0).all() and (r.niter.cpu().numpy() == 0).all()
+    assert np.array_equal(r.params.cpu().numpy(), p0)
+    # noise-free 11x11 Gaussians from a perturbed start: the generating parameters come back
+    rng = np.random.default_rng(9)
+    n = 256
+    truth = np.stack([rng.uniform(50, 500, n), rng.uniform(500, 5000, n), rng.uniform(4.2, 5.8, n),
+                      rng.uniform(4.2, 5.8, n), rng.uniform(1.0, 2.0, n), rng.uniform(1.0, 2.0, n),
+                      rng.uniform(10, 80, n)], axis=1)
+    wins = np.stack([po.gauss2d(p, (11, 11)) for p in truth])
+    p0 = truth * rng.uniform(0.9, 1.1, truth.shape)
+    lo = np.zeros((n, 7))
+    hi = np.tile(np.array([0, 0, 0, 0, 0, 0, 360.]), (n, 1))
+    lmin = np.tile(np.array([0, 0, 0, 0, 1, 1, 1], dtype=np.uint8), (n, 1))
+    lmax = np.tile(np.array([0, 0, 0, 0, 0, 0, 1], dtype=np.uint8), (n, 1))
+    r = engine.gaussfit_batch(wins, p0, lo, hi, lmin, lmax, solver="fast")
+    good = agree(r.params.cpu().numpy(), truth, tol=1e-6, ctol=1e-6)
+    assert (r.status.cpu().numpy() > 0).all() and good.mean() > 0.93
+    # a window size the FAST solver does not take is refused, not silently re-routed
+    with pytest.raises(ValueError):
+        engine.gaussfit_batch(np.zeros((1, 7, 7)), p0[:1], lo[:1], hi[:1], lmin[:1], lmax[:1], solver="fast")
