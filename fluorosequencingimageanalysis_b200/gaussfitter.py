@@ -100,6 +100,8 @@ class MpfitResult(object):
 
 
 FAITHFUL = True
+#: "minpack" (the reference's algorithm, default) or "fast" (the production fitter) -- see pflib.SOLVER
+SOLVER = "minpack"
 
 
 def gaussfit(data, err=None, params=(), autoderiv=True, return_all=False, circle=False,
