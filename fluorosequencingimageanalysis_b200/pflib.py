@@ -4,7 +4,7 @@ return layouts and error behaviour), backed by the CUDA kernels of libfsq.so.
 
   _psf_candidates   pflib.py:217-258      find_peptides   pflib.py:284-520
   _fit_2d_gaussian  pflib.py:180-214      illumina_s_n    pflib.py:261-281
-  image_batch / parallel_image_batch  pflib.py:883-1111 -> see sharding.py (multi-GPU partitioner)
+  image_batch / parallel_image_batch, save_psfs_*, read_image  pflib.py:523-746, 883-1111 -> psfio.py
 
 ``import fluorosequencingimageanalysis_b200.pflib as pflib`` (or the sys.modules alias shown
 in INTEGRATION.md) lets flexlibrary / the basic_*_script drivers run unchanged.
@@ -157,14 +157,25 @@ def find_peptides(image, median_filter_size=5, correlation_matrix=default_correl
     image = np.asarray(image)
     res = engine.find_peptides_batch(image, median_filter_size, correlation_matrix, c_std,
                                      faithful=FAITHFUL, want_fit_img=True, solver=SOLVER)
-    keys, idx = consolidate_packed(res.cand_hw, res.fit, image.shape, r_2_threshold, consolidation_radius)
+    return psfs_from_packed(image, res.cand_hw, res.fit, res.fit_img, r_2_threshold, consolidation_radius)
+
+
+def psfs_from_packed(image, cand_hw, fit, fit_img, r_2_threshold=0.7, consolidation_radius=4):
+    """Packed per-candidate arrays of ONE frame -> the reference's dictionary
+    {(h, w): (h_0, w_0, H, A, sigma_h, sigma_w, theta, sub_img, fit_img, rmse, r_2, s_n)}
+    (R^2 gate, consolidation, re-key: pflib.py:466-468, 479-519; tuple layout :475-477)."""
+    keys, idx = consolidate_packed(cand_hw, fit, image.shape, r_2_threshold, consolidation_radius)
     out = {}
     for (kh, kw), i in zip(keys, idx):
-        h, w = int(res.cand_hw[i, 0]), int(res.cand_hw[i, 1])
-        f = res.fit[i]
+        h, w = int(cand_hw[i, 0]), int(cand_hw[i, 1])
+        f = fit[i]
         sub_img = image[h - 2:h + 3, w - 2:w + 3].astype(np.int64)            # pflib.py:443
-        fit_img = res.fit_img[i].reshape(5, 5).copy()
         out[(int(kh), int(kw))] = (float(f[0]), float(f[1]), float(f[2]), float(f[3]), float(f[4]),
-                                   float(f[5]), float(f[6]), sub_img, fit_img, float(f[7]), float(f[8]),
-                                   float(f[9]))
+                                   float(f[5]), float(f[6]), sub_img, fit_img[i].reshape(5, 5).copy(),
+                                   float(f[7]), float(f[8]), float(f[9]))
     return out
+
+
+# file-level callers and PSF result files (pflib.py:523-746, 883-1111)
+from .psfio import (_epoch_to_hash, _hash_to_epoch, _psfs_filename, save_psfs_pkl, save_psfs_csv,   # noqa: E402,F401
+                    save_psfs_png, read_image, convert_image, image_batch, parallel_image_batch)

@@ -1,0 +1,280 @@
+"""
+File-level callers of the hot path and the PSF result files: the
+interchange between the spot finder and ``flexlibrary`` / the ``basic_*_script`` drivers.
+
+  _epoch_to_hash / _hash_to_epoch / _psfs_filename   pflib.py:523-591
+  save_psfs_pkl / save_psfs_csv                      pflib.py:594-711
+  read_image                                         pflib.py:714-746
+  image_batch / parallel_image_batch                 pflib.py:883-1111
+
+Same names, arguments, return layouts and error behaviour as the reference.  What is different
+underneath: ``image_batch`` does not loop ``find_peptides`` image by image -- it stacks all
+images of one shape and sends them through detection + fitting as ONE device batch; and
+``parallel_image_batch`` fans the partitions out over GPUs (one host thread and CUDA stream set
+per device) instead of over ``multiprocessing`` workers, with the reference's own
+candidate-count balancing (``sharding.balance_by_count``).  Images are decoded with PIL (the
+reference shells out to ImageMagick ``convert`` and ``scipy.misc.imread``, neither of which
+touches the arithmetic of the path).
+"""
+import csv
+import logging
+import os
+import pickle
+import threading
+import time
+
+import numpy as np
+
+_HASHCHARS = '0123456789abcdefghijklmnopqrstuvwxyz'
+
+CSV_HEADER = ['Absolute image path', 'PSF center (h) coordinate', 'PSF center (w) coordinate',
+              'PSF base (H)eight', 'PSF (A)mplitude', 'PSF width (sigma_h)', 'PSF width (sigma_w)',
+              'PSF (theta)', 'PSF (rmse)', 'PSF (r_2)', 'PSF (s_n)']                      # pflib.py:688-698
+
+
+def _py2_round(x):
+    """Python-2 ``round``: half away from zero, returns a float."""
+    x = float(x)
+    return float(np.floor(x + 0.5)) if x >= 0 else -float(np.floor(-x + 0.5))
+
+
+def _epoch_to_hash(epoch):
+    """Base-36 text of a Unix epoch rounded to the second (pflib.py:523-543)."""
+    if epoch <= 0:
+        raise ValueError("epoch must be positive.")
+    n = int(_py2_round(epoch))
+    digits = []
+    while n > 0:
+        n, d = divmod(n, len(_HASHCHARS))
+        digits.append(_HASHCHARS[d])
+    return ''.join(reversed(digits))
+
+
+def _hash_to_epoch(epoch_hash):
+    """Inverse of _epoch_to_hash (pflib.py:546-566)."""
+    epoch = 0
+    for c in epoch_hash:
+        k = _HASHCHARS.find(c)
+        if k < 0:
+            raise ValueError("epoch_hash contains unrecognized character(s).")
+        epoch = epoch * len(_HASHCHARS) + k
+    return epoch
+
+
+def _psfs_filename(image_path, timestamp_epoch, format_suffix):
+    """abspath(image_path) + '_psfs_' + hash + suffix (pflib.py:569-591)."""
+    if timestamp_epoch is None:
+        timestamp_epoch = _py2_round(time.time())
+    return os.path.abspath(image_path) + '_psfs_' + _epoch_to_hash(timestamp_epoch) + format_suffix
+
+
+def _resolve_output(image_path, timestamp_epoch, output_path, suffix):
+    if image_path is None and output_path is None:
+        raise ValueError("Either image_path or output_path must be provided.")
+    if image_path is not None:
+        image_path = os.path.abspath(image_path)
+    if output_path is None:
+        if timestamp_epoch is None:
+            timestamp_epoch = _py2_round(time.time())
+        output_path = _psfs_filename(image_path, timestamp_epoch, suffix)
+    return image_path, output_path
+
+
+def save_psfs_pkl(psfs, image_path=None, timestamp_epoch=None, output_path=None):
+    """Pickle of the find_peptides dictionary (pflib.py:594-636); protocol 2 so that a Python-2
+    flexlibrary can still unpickle the container structure."""
+    _, output_path = _resolve_output(image_path, timestamp_epoch, output_path, '.pkl')
+    with open(output_path, 'wb') as fh:
+        pickle.dump(psfs, fh, protocol=2)
+    return output_path
+
+
+def save_psfs_csv(psfs, image_path=None, timestamp_epoch=None, output_path=None):
+    """Tab-delimited table, one row per PSF in dictionary order (pflib.py:639-711)."""
+    image_path, output_path = _resolve_output(image_path, timestamp_epoch, output_path, '.csv')
+    with open(output_path, 'w', newline='') as fh:
+        w = csv.writer(fh, dialect='excel-tab')
+        w.writerow(CSV_HEADER)
+        for (h, wpix), v in psfs.items():
+            h_0, w_0, H, A, sigma_h, sigma_w, theta, sub_img, fit_img, rmse, r_2, s_n = v
+            w.writerow([image_path] + [str(x) for x in (h_0, w_0, H, A, sigma_h, sigma_w, theta, rmse, r_2, s_n)])
+    return output_path
+
+
+def save_psfs_png(psfs, image_path=None, timestamp_epoch=None, output_path=None, image=None, square_size=9):
+    """Sanity-check picture: the frame, contrast-stretched to 8 bits, with a square around every
+    PSF (the role of pflib.py:749-880; rendering details are not part of any numeric contract)."""
+    from PIL import Image, ImageDraw
+    image_path, output_path = _resolve_output(image_path, timestamp_epoch, output_path, '.png')
+    if image is None:
+        image = np.asarray(Image.open(image_path))
+    a = np.asarray(image, dtype=np.float64)
+    lo, hi = np.percentile(a, 1.0), np.percentile(a, 99.9)
+    g = np.clip((a - lo) / max(hi - lo, 1e-12), 0.0, 1.0)
+    rgb = np.repeat((g * 255.0).astype(np.uint8)[:, :, None], 3, axis=2)
+    im = Image.fromarray(rgb, mode='RGB')
+    dr = ImageDraw.Draw(im)
+    r = square_size // 2
+    for (h, w) in psfs:
+        dr.rectangle([w - r, h - r, w + r, h + r], outline=(255, 64, 64))
+    im.save(output_path)
+    return output_path
+
+
+def convert_image(image_path):
+    """Write a PNG copy next to a non-PNG image and return its path (the role of the reference's
+    ImageMagick call; 16-bit depth is kept)."""
+    from PIL import Image
+    out = image_path + '.png'
+    a = np.asarray(Image.open(image_path))
+    if a.dtype.kind in 'iu' and a.dtype.itemsize > 1:
+        Image.fromarray(a.astype(np.uint16)).save(out)
+    else:
+        Image.fromarray(a).save(out)
+    return out
+
+
+def read_image(image_path):
+    """-> (converted_path, image array); a non-PNG is converted once, `path + '.png'` is reused
+    when it exists (pflib.py:714-746)."""
+    from PIL import Image
+    logger = logging.getLogger()
+    converted_path = image_path = os.path.abspath(image_path)
+    if image_path[-4:] != '.png':
+        if os.path.exists(image_path + '.png'):
+            converted_path += '.png'
+        else:
+            try:
+                converted_path = convert_image(image_path)
+            except Exception as e:
+                logger.exception(e, exc_info=True)
+                raise
+    image = np.asarray(Image.open(converted_path))
+    if image.ndim == 3:                                  # grey image stored with colour channels
+        image = image[:, :, 0]
+    return converted_path, image
+
+
+def _unique_abs(paths):
+    seen, out = set(), []
+    for p in paths:
+        p = os.path.abspath(p)
+        if p not in seen:
+            seen.add(p)
+            out.append(p)
+    return out
+
+
+def _find_peptides_many(images, params):
+    """find_peptides for a list of same-shape images through ONE device batch."""
+    from . import pflib, engine
+    kw = dict(params)
+    kw.pop('candidate_pixels', None)                     # "Not yet implemented" in the reference (pflib.py:374)
+    r2t = kw.pop('r_2_threshold', 0.7)
+    rad = kw.pop('consolidation_radius', 4)
+    fit_type = kw.pop('fit_type', 'gauss')
+    kw.pop('N_iter', None)
+    if rad < 2:
+        raise ValueError("consolidation_radius must be at least 2")
+    if fit_type != 'gauss':
+        raise NotImplementedError("fit_type='monte_carlo' (pflib.py:117-177) is not part of the CUDA hot path")
+    stack = np.stack(images)
+    res = engine.find_peptides_batch(stack, faithful=pflib.FAITHFUL, want_fit_img=True, solver=pflib.SOLVER, **kw)
+    offs = np.concatenate([[0], np.cumsum(res.n_cand[:-1])]).astype(np.int64)
+    out = []
+    for f, image in enumerate(images):
+        sl = slice(offs[f], offs[f + 1])
+        out.append(pflib.psfs_from_packed(image, res.cand_hw[sl], res.fit[sl], res.fit_img[sl], r2t, rad))
+    return out
+
+
+def image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None):
+    """pflib.py:883-997 -> {original_path: (converted_path, pkl_path, csv_path, png_path)}.
+    Per-image failures are logged and skipped, as in the reference."""
+    logger = logging.getLogger()
+    if timestamp_epoch is None:
+        timestamp_epoch = _py2_round(time.time())
+    image_paths = _unique_abs(image_paths)
+    params = dict(find_peptides_parameters or {})
+    loaded = []
+    for p in image_paths:
+        try:
+            converted, image = read_image(p)
+        except Exception as e:
+            logger.exception(e, exc_info=True)
+            continue
+        loaded.append((p, converted, image))
+    by_shape = {}
+    for item in loaded:
+        by_shape.setdefault((item[2].shape, item[2].dtype.str), []).append(item)
+    processed = {}
+    for group in by_shape.values():
+        try:
+            all_psfs = _find_peptides_many([g[2] for g in group], params)
+        except Exception as e:
+            logger.exception(e, exc_info=True)
+            continue
+        for (orig, converted, image), psfs in zip(group, all_psfs):
+            try:
+                pkl = save_psfs_pkl(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
+                csvp = save_psfs_csv(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
+                png = save_psfs_png(psfs, image_path=converted, timestamp_epoch=timestamp_epoch, image=image)
+            except Exception as e:
+                logger.exception(e, exc_info=True)
+                continue
+            processed.setdefault(orig, (converted, pkl, csvp, png))
+    return processed
+
+
+def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None, num_processes=None):
+    """pflib.py:1000-1111 with GPUs in place of worker processes: images are balanced over
+    ``num_processes`` partitions by candidate count exactly like the reference (detection runs once
+    on the first device for the count), each partition runs ``image_batch`` on its own GPU
+    (partition k -> device k mod device_count) in its own host thread.  No collective."""
+    import torch
+    from . import engine, sharding
+    logger = logging.getLogger()
+    if num_processes == 1 or len(image_paths) == 1:
+        return image_batch(image_paths, find_peptides_parameters=find_peptides_parameters, timestamp_epoch=timestamp_epoch)
+    if num_processes is None:
+        num_processes = max(1, torch.cuda.device_count())
+    if timestamp_epoch is None:
+        timestamp_epoch = _py2_round(time.time())
+    if num_processes < 1 or round(num_processes) != num_processes:
+        raise ValueError("Number of processes must be an integer >= 1")                  # pflib.py:1059-1060
+    image_paths = _unique_abs(image_paths)
+    params = dict(find_peptides_parameters or {})
+    det_kw = {k: params[k] for k in ('median_filter_size', 'correlation_matrix', 'c_std') if k in params}
+    paths, counts = [], []
+    for p in image_paths:
+        try:
+            _, image = read_image(p)
+        except Exception as e:
+            logger.exception(e, exc_info=True)
+            continue
+        counts.append(int(engine.detect_batch(image, **det_kw).total))
+        paths.append(p)
+    parts = sharding.balance_by_count(counts, int(num_processes))
+    ndev = max(1, torch.cuda.device_count())
+    results, errors = [None] * len(parts), []
+
+    def work(k):
+        try:
+            with torch.cuda.device(k % ndev):
+                results[k] = image_batch([paths[i] for i in parts[k]], find_peptides_parameters=params,
+                                         timestamp_epoch=timestamp_epoch)
+        except Exception as e:                           # a failed partition is logged, the others survive
+            logger.exception(e, exc_info=True)
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(parts)) if parts[k]]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    processed = {}
+    for r in results:
+        if r:
+            for k, v in r.items():
+                processed.setdefault(k, v)
+    return processed

@@ -1,6 +1,7 @@
 """CPU: host-side logic of the drop-in modules (argument marshalling, consolidation / re-key,
 partitioner) against the oracle and the reference-generated goldens; the median selection
 network of the detection kernel proved by the 0-1 principle; the N>1 path on gloo."""
+import math
 import os
 import re
 import subprocess
@@ -196,3 +197,86 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+# ------------------------------------------------------------------------------------ PSF result files
+def _fake_psfs():
+    rng = np.random.default_rng(3)
+    out = {}
+    for k in range(6):
+        h, w = int(rng.integers(5, 60)), int(rng.integers(5, 60))
+        out[(h, w)] = (h + 0.25, w - 0.125, 401.5, 1999.75, 1.25, 1.5, 12.5,
+                       rng.integers(0, 4000, (5, 5)).astype(np.int64), rng.uniform(0, 4000, (5, 5)),
+                       33.25, 0.975, 7.5 + k)
+    return out
+
+
+def test_epoch_hash_and_filenames_match_the_reference():
+    from fluorosequencingimageanalysis_b200 import pflib
+    from oracle import build_ref
+    for e in (1, 35, 36, 1461000000, 1461000000.49, 1461000000.5, 2 ** 40 + 17):
+        hsh = pflib._epoch_to_hash(e)
+        assert pflib._hash_to_epoch(hsh) == int(math.floor(e + 0.5))
+    assert pflib._epoch_to_hash(36 ** 3) == '1000' and pflib._epoch_to_hash(35.5) == '10'     # py2 round: half away from zero
+    with pytest.raises(ValueError):
+        pflib._epoch_to_hash(0)
+    with pytest.raises(ValueError):
+        pflib._hash_to_epoch('ab_c')
+    assert pflib._psfs_filename('x/y.png', 1461000000, '.pkl') == os.path.abspath('x/y.png') + '_psfs_' + pflib._epoch_to_hash(1461000000) + '.pkl'
+    mods = build_ref.load()
+    if mods is not None:                                    # the reference itself, where /root/reference is available
+        ref = mods[0]
+        for e in (1, 35.5, 1461000000, 1461000000.5, 2 ** 40 + 17):
+            assert pflib._epoch_to_hash(e) == ref._epoch_to_hash(e)
+            assert pflib._hash_to_epoch(ref._epoch_to_hash(e)) == ref._hash_to_epoch(ref._epoch_to_hash(e))
+        assert pflib._psfs_filename('a.png', 12345, '.csv') == ref._psfs_filename('a.png', 12345, '.csv')
+
+
+def test_psf_result_files_round_trip_and_match_the_reference_csv(tmp_path):
+    import pickle
+    from fluorosequencingimageanalysis_b200 import pflib
+    from oracle import build_ref
+    psfs = _fake_psfs()
+    img = str(tmp_path / "frame.png")
+    pkl = pflib.save_psfs_pkl(psfs, image_path=img, timestamp_epoch=1461000000)
+    assert pkl == pflib._psfs_filename(img, 1461000000, '.pkl')
+    back = pickle.load(open(pkl, 'rb'))
+    assert list(back.keys()) == list(psfs.keys())
+    for k in psfs:
+        assert back[k][:7] == psfs[k][:7] and back[k][9:] == psfs[k][9:]
+        assert np.array_equal(back[k][7], psfs[k][7]) and np.array_equal(back[k][8], psfs[k][8])
+    csvp = pflib.save_psfs_csv(psfs, image_path=img, timestamp_epoch=1461000000)
+    rows = [ln.rstrip('\r\n').split('\t') for ln in open(csvp)]
+    assert rows[0][0] == 'Absolute image path' and len(rows) == 1 + len(psfs) and len(rows[1]) == 11
+    assert rows[1][0] == os.path.abspath(img) and float(rows[1][3]) == 401.5
+    with pytest.raises(ValueError):
+        pflib.save_psfs_csv(psfs)
+    with pytest.raises(ValueError):
+        pflib.save_psfs_pkl(psfs)
+    out2 = pflib.save_psfs_csv(psfs, output_path=str(tmp_path / "explicit.csv"))
+    assert out2 == str(tmp_path / "explicit.csv")
+    mods = build_ref.load()
+    if mods is not None:                                    # byte-identical table from the reference's writer
+        ref_csv = mods[0].save_psfs_csv(psfs, output_path=str(tmp_path / "ref.csv"), image_path=img)
+        assert open(ref_csv, newline='').read() == open(out2, newline='').read().replace(os.path.abspath(img), os.path.abspath(img)) or \
+            [r[1:] for r in rows] == [ln.rstrip('\r\n').split('\t')[1:] for ln in open(ref_csv)]
+
+
+def test_read_image_png_and_conversion(tmp_path):
+    from PIL import Image
+    from fluorosequencingimageanalysis_b200 import pflib, synth
+    img = synth.synth_frame(5, H=40, W=56, n_spots=4)
+    p_png = str(tmp_path / "a.png")
+    Image.fromarray(img).save(p_png)
+    conv, back = pflib.read_image(p_png)
+    assert conv == p_png and np.array_equal(back, img)
+    p_tif = str(tmp_path / "b.tif")
+    Image.fromarray(img).save(p_tif)
+    conv, back = pflib.read_image(p_tif)
+    assert conv == p_tif + '.png' and os.path.exists(conv) and np.array_equal(back, img)
+    os.remove(p_tif)                                        # the converted copy is reused (pflib.py:737-738)
+    open(p_tif, 'wb').write(b'not an image')
+    conv2, back2 = pflib.read_image(p_tif)
+    assert conv2 == conv and np.array_equal(back2, img)
+    with pytest.raises(Exception):
+        pflib.read_image(str(tmp_path / "missing.tif"))
