@@ -267,15 +267,14 @@ def run_ours(args):
     stacks_dev = [t.to(dev) for t in stacks_host]
     in_bytes = N_FRAMES * H * W * 2
     kw = dict(dtype=torch.uint16, faithful=faithful, solver=solver)
+    if args.park is not None:
+        kw["park_after"] = args.park
+    kw["warps_per_sm"] = args.warps_per_sm
     cur = torch.cuda.current_stream()
 
     # ---- timed region A: inputs resident in HBM; K steps software-pipelined over `depth` streams
     fs = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=False, **kw)
     totals = torch.zeros(max(args.steps, warmup), dtype=torch.int64, device=dev)
-    if args.park is not None:
-        kw["park_after"] = args.park
-    if args.ctas_per_sm is not None:
-        kw["ctas_per_sm"] = args.ctas_per_sm
 
     def resident_steps(n_steps, first):
         for k in range(n_steps):
@@ -344,23 +343,26 @@ def run_ours(args):
     fe = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=True, **kw)
 
     def e2e_steps(n_steps, first):
+        # submit(k), begin_fetch(k - depth + 2), end_fetch(k - depth + 1): depth - 1 batches stay in flight,
+        # the host never waits for the batch it has just queued
         fits = d2h = 0
         tick = []
+        lag_b, lag_e = max(args.depth - 2, 1), max(args.depth - 1, 2)
         for k in range(n_steps):
             tick.append(fe.submit(stacks_host[(first + k) % N_VARIANTS]))
-            if k >= 1:
-                fe.begin_fetch(tick[k - 1])
-            if k >= 2:
-                n = fe.end_fetch(tick[k - 2])[0]
+            if k >= lag_b:
+                fe.begin_fetch(tick[k - lag_b])
+            if k >= lag_e:
+                n = fe.end_fetch(tick[k - lag_e])[0]
                 fits += n
                 d2h += pipe.d2h_bytes(n)
-        for t in tick[max(0, n_steps - 2):]:
+        for t in tick[max(0, n_steps - lag_e):]:
             n = fe.end_fetch(t)[0]
             fits += n
             d2h += pipe.d2h_bytes(n)
         return fits, d2h
 
-    e2e_steps(3, 0)
+    e2e_steps(max(3, args.depth), 0)
     barrier()
     t0 = time.perf_counter()
     e2e_fits, d2h = e2e_steps(args.steps, 2)
@@ -459,7 +461,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots (sigma 1.5), every frame: "
                                "detection + 5x5 LM fit of every candidate + metrics",
                    "frames_per_step": N_FRAMES, "candidates_per_step": n_probe,
-                   "solver": args.solver, "pipeline_depth": args.depth,
+                   "solver": args.solver, "pipeline_depth": args.depth, "lm_warps_per_sm_per_batch": args.warps_per_sm,
                    "l2": "8 different stacks cycled (168 MB > 126 MB L2): inputs larger than L2", "parallelism": "field-sharded x%d, no collective" % world},
         "frames_per_s": frames_per_s, "serial_ms_per_step": serial_ms_per_step,
         "host_enqueue_ms_per_step": host_enqueue_ms,
@@ -486,10 +488,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="fast", choices=["fast", "fast64", "minpack-faithful", "minpack-clean"])
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (streams) in the pipelined regions")
+    ap.add_argument("--depth", type=int, default=5, help="batches in flight (streams) in the pipelined regions")
     ap.add_argument("--no-parity-solver", action="store_true")
     ap.add_argument("--park", type=int, default=None, help="fsq_lm_opts.park_after override (scheduling only)")
-    ap.add_argument("--ctas-per-sm", type=int, default=None, help="fsq_lm_opts.ctas_per_sm override (scheduling only)")
+    ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
+                    help="fsq_lm_opts.warps_per_sm: warps per SM of ONE batch's LM launch (scheduling only; 0 = fill the SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

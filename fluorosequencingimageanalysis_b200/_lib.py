@@ -28,7 +28,7 @@ class LmOpts(_c.Structure):
     _fields_ = [("ftol", _c.c_double), ("xtol", _c.c_double), ("gtol", _c.c_double),
                 ("factor", _c.c_double), ("maxiter", _c.c_int32), ("faithful", _c.c_int32),
                 ("want_perror", _c.c_int32), ("solver", _c.c_int32),
-                ("park_after", _c.c_int32), ("ctas_per_sm", _c.c_int32)]
+                ("park_after", _c.c_int32), ("warps_per_sm", _c.c_int32)]
 
 
 class FsqError(RuntimeError):

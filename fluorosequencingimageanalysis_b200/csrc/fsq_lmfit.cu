@@ -974,7 +974,7 @@ using namespace fsq;
 extern "C" void fsq_lm_default_opts(fsq_lm_opts* o) {
     if (!o) return;
     o->ftol = 1e-10; o->xtol = 1e-10; o->gtol = 1e-10; o->factor = 100.0; o->maxiter = 200;   // mpfit.py:600-605
-    o->faithful = 1; o->want_perror = 0; o->solver = FSQ_SOLVER_MINPACK; o->park_after = 0; o->ctas_per_sm = 0;
+    o->faithful = 1; o->want_perror = 0; o->solver = FSQ_SOLVER_MINPACK; o->park_after = 0; o->warps_per_sm = 0;
 }
 
 static int check_opts(const fsq_lm_opts* o, const char* who) {

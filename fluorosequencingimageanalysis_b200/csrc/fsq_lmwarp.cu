@@ -795,7 +795,7 @@ long long warp_scratch_bytes(long long n) { return 64 + (long long)sizeof(StragR
 // Persistent launch(es) of one kernel flavour: phase 1 over every fit (parked after `park_after`
 // passes when that is set), phase 2 over the parked fits.
 template <int WIN, int TPB, int MINB, bool PFLIB>
-static int launch_warp(WarpArgs& a, const fsq_lm_opts* opts, unsigned long long* head, cudaStream_t st) {
+static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
     constexpr size_t smem = (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
     static int per_sm = 0;
     if (per_sm == 0) {
@@ -804,14 +804,15 @@ static int launch_warp(WarpArgs& a, const fsq_lm_opts* opts, unsigned long long*
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB>, TPB, smem) != cudaSuccess || v < 1) v = 1;
         per_sm = v;
     }
-    const int use_per_sm = (opts->ctas_per_sm > 0 && opts->ctas_per_sm < per_sm) ? opts->ctas_per_sm : per_sm;
+    const int use_per_sm = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
     long long blocks = (long long)sm_count() * use_per_sm;
     const long long need = (a.n + TPB - 1) / TPB;
     if (need < blocks) blocks = need < 1 ? 1 : need;
-    a.cap = opts->park_after > 0 ? opts->park_after : 0; a.resume = 0;
+    const int park = a.o.park_after > 0 ? a.o.park_after : 0;
+    a.cap = park; a.resume = 0;
     lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks, TPB, smem, st>>>(a);
     FSQ_LAUNCH_CHECK();
-    if (a.cap > 0) {
+    if (park > 0) {
         FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
         a.cap = 0; a.resume = 1;
         // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
@@ -821,6 +822,17 @@ static int launch_warp(WarpArgs& a, const fsq_lm_opts* opts, unsigned long long*
         FSQ_LAUNCH_CHECK();
     }
     return FSQ_OK;
+}
+
+// Persistent launch of the frame-path kernel with `warps_per_sm` warps per SM (fsq.h): block size and
+// blocks per SM are chosen so that the register budget per thread stays the same (221 registers).
+static int launch_frame_path(WarpArgs& a, unsigned long long* head, cudaStream_t st) {
+    switch (a.o.warps_per_sm) {
+        case 1:  return launch_warp<5, 32, 8, true>(a, 1, head, st);
+        case 2:  return launch_warp<5, 64, 4, true>(a, 1, head, st);
+        case 4:  return launch_warp<5, WTHREADS, WMINB, true>(a, 1, head, st);
+        default: return launch_warp<5, WTHREADS, WMINB, true>(a, 0, head, st);
+    }
 }
 
 int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const int32_t* cand_hw,
@@ -836,7 +848,7 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     fit_prep_kernel<<<flat, 128, 0, st>>>(a);
     FSQ_LAUNCH_CHECK();
-    const int rc = launch_warp<5, WTHREADS, WMINB, true>(a, opts, head, st);
+    const int rc = launch_frame_path(a, head, st);
     if (rc != FSQ_OK) return rc;
     if (fit_img) {
         fit_image_kernel<<<flat, 128, 0, st>>>(a);
@@ -865,8 +877,9 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);
     FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     int rc;
-    if (win == 5) rc = launch_warp<5, 128, 3, false>(a, &o, head, st);
-    else if (win == 11) rc = launch_warp<11, 64, 3, false>(a, &o, head, st);
+    a.o = o;
+    if (win == 5) rc = launch_warp<5, 128, 2, false>(a, 0, head, st);
+    else if (win == 11) rc = launch_warp<11, 64, 3, false>(a, 0, head, st);
     else { set_error("the FAST solver takes 5x5 or 11x11 windows (got %d)", win); rc = FSQ_E_ARG; }
     cudaFreeAsync(scratch, st);
     if (rc != FSQ_OK) return rc;

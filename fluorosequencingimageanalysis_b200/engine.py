@@ -330,7 +330,7 @@ class FieldPipeline(object):
 
     def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
                  median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
-                 device=None, solver="fast", park_after=None, ctas_per_sm=None):
+                 device=None, solver="fast", park_after=None, warps_per_sm=None):
         require_cuda()
         self.L = _lib.load()
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -342,7 +342,7 @@ class FieldPipeline(object):
         self.K = _check_kernel(correlation_matrix)
         self.mf = int(median_filter_size)
         self.c_std = float(c_std)
-        self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after, ctas_per_sm=ctas_per_sm)
+        self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after, warps_per_sm=warps_per_sm)
         self.solver = solver
         if cap_per_frame is None:
             cap_per_frame = max(1024, int(0.06 * H * W))
@@ -428,8 +428,9 @@ class FieldStream(object):
         fs.begin_fetch(t)              # waits for the candidate count, queues the D2H of exactly n rows
         n, hw, frame, fit, ints = fs.end_fetch(t)     # views into the slot's pinned buffers
 
-    Call order for full overlap: submit(k); begin_fetch(k-1); end_fetch(k-2).  A slot is reused
-    after ``depth`` submits; its previous results must have been fetched (or abandoned) by then."""
+    Call order for full overlap: submit(k); begin_fetch(k - depth + 2); end_fetch(k - depth + 1) -- the
+    host then never waits for a batch it has just queued.  A slot is reused after ``depth`` submits; its
+    previous results must have been fetched (or abandoned) by then."""
 
     def __init__(self, n_frames, H, W, dtype=None, depth=3, host_io=True, **kw):
         require_cuda()

@@ -101,10 +101,12 @@ typedef struct fsq_lm_opts {
                            finished by a second launch over the parked fits, so that a handful of
                            100+-iteration fits do not pin whole thread blocks.  0 = one launch
                            (default; on B200 the two-launch schedule measured no faster).   */
-    int32_t ctas_per_sm;/* FAST solver scheduling only: thread blocks per SM of the persistent LM launch.
-                           0 = as many as fit (3).  1 leaves two thirds of every SM to launches queued on
-                           other streams: with several batches in flight (engine.FieldStream) each
-                           batch's long-fit tail then runs underneath the other batches' bulk.    */
+    int32_t warps_per_sm;/* FAST solver scheduling only: warps per SM of the persistent LM launch: 8 (= 0,
+                           the default: the launch fills the machine), 4, 2 or 1.  A small value leaves
+                           most of every SM to launches queued on other streams: with several batches in
+                           flight (engine.FieldStream) each thread then works through many more fits, so
+                           far fewer warp-ticks are spent on half-empty warps waiting for their last long
+                           fit, and one batch's tail runs underneath the other batches' bulk.        */
 } fsq_lm_opts;
 
 /* Solvers behind the two fit entry points.

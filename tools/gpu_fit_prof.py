@@ -18,7 +18,7 @@ ts = []
 for rep in range(reps):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    o = _lib.default_opts(faithful=faithful, solver=solver, ctas_per_sm=int(os.environ.get("FSQ_CTAS", "0")),
+    o = _lib.default_opts(faithful=faithful, solver=solver, warps_per_sm=int(os.environ.get("FSQ_WARPS", "0")),
                           park_after=int(os.environ.get("FSQ_PARK", "0")), maxiter=int(os.environ.get("FSQ_MAXITER", "200")))
     fit, ints, _ = engine.fit_candidates(frd, det.cand_hw, det.cand_frame, det.total, opts=o)
     e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
