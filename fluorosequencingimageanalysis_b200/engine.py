@@ -55,6 +55,8 @@ def to_device_frames(frames, device=None):
     device = device or torch.device("cuda", torch.cuda.current_device())
     if isinstance(frames, np.ndarray):
         a = frames
+        if not a.flags.writeable:                      # e.g. arrays decoded by PIL: torch wants a writable buffer
+            a = a.copy()
         if a.dtype == np.uint16:
             t = torch.from_numpy(a.view(np.int16)).view(torch.uint16)
         elif a.dtype in (np.uint8, np.int16, np.int32):

@@ -91,22 +91,23 @@ def test_fast_metrics_and_fit_image(fast5, frame0):
 
 
 def test_fast_scheduling_never_changes_a_result(frame0):
-    """park_after (two-launch scheduling of long fits), batch composition and batch order are
-    scheduling only: bit-identical parameters, metrics and counters."""
+    """park_after (two-launch scheduling of long fits), warps_per_sm (launch geometry: 32-, 64- and
+    128-thread blocks), batch composition and batch order are scheduling only: bit-identical
+    parameters, metrics and counters."""
     engine, _, synth, _lib = _mods()
     import torch
     stack = np.stack([frame0, synth.synth_frame(3), frame0])
     frd = engine.to_device_frames(stack)
     det = engine.detect_batch(frd)
     base = None
-    for park in (0, 8, 32):
-        o = _lib.default_opts(faithful=False, solver="fast", park_after=park)
+    for park, wps in ((0, 0), (8, 0), (32, 0), (0, 4), (0, 2), (0, 1), (16, 2)):
+        o = _lib.default_opts(faithful=False, solver="fast", park_after=park, warps_per_sm=wps)
         fit, ints, _ = engine.fit_candidates(frd, det.cand_hw, det.cand_frame, det.total, opts=o)
         fit, ints = fit.cpu().numpy(), ints.cpu().numpy()
         if base is None:
             base = (fit, ints)
         else:
-            assert np.array_equal(base[0].view(np.int64), fit.view(np.int64)), "park_after=%d changed a fit" % park
+            assert np.array_equal(base[0].view(np.int64), fit.view(np.int64)), "park_after=%d warps_per_sm=%d changed a fit" % (park, wps)
             assert np.array_equal(base[1], ints)
     # frame 0 and frame 2 hold the same pixels: same fits, shifted by nothing
     n = det.n_cand.cpu().numpy()
