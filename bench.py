@@ -422,25 +422,34 @@ def run_ours(args):
             hbm_src = "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    lm_traffic = traffic.get("lmwarp_kernel", {}).get("bytes") if solver == "fast" else None
+    det_traffic = traffic.get("detect_cm_packed_kernel", {}).get("bytes")
     det_bytes = N_FRAMES * H * W * 2 + 8 * n_last
     det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
     kname = {"fast": "lmwarp_kernel phase 1 + phase 2 (+ fit_prep_kernel) behind fsq_fit_candidates",
              "fast64": "lmfast_kernel<double,true>", "minpack": "lmfit_kernel<8,true>"}[solver]
     roofline = {"bound": pk, "achieved": achieved, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (peak[pk] / 1e12), "traffic": None,
+                "frac": achieved / (peak[pk] / 1e12), "traffic": lm_traffic,
+                "achieved_in_pipeline": flops / n_last * (fits_all / world / args.steps) / (ms_total / args.steps * 1e-3) / 1e12,
                 "kernel": kname, "ms_per_launch": fit_ms_avg,
                 "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "passes_per_launch": sum_nfev,
                 "flop_per_lm_iteration": fl_iter,
                 "peak_source": "fsq_fma_peak %s FMA micro-benchmark, measured in this run (of measured)" % pk.upper(),
                 "fp32_fma_peak_tflops": peak["fp32"] / 1e12, "fp64_fma_peak_tflops": peak["fp64"] / 1e12,
                 "share_of_serial_step": fit_ms_avg / serial_ms_per_step,
-                "note": "FLOPs by the SURVEY 8(d) convention; the kernel keeps residual/chi^2 in FP64 and the "
-                        "Jacobian / normal equations / Cholesky in FP32, so the FP32 peak is an upper bound it cannot reach"}
+                "note": "FLOPs by the SURVEY 8(d) convention; achieved = fit launches of one batch timed alone (CUDA events), "
+                        "achieved_in_pipeline = the same FLOPs over the whole pipelined step; the kernel keeps residual/chi^2 in "
+                        "FP64 and the Jacobian / normal equations / Cholesky in FP32, so the FP32 peak is an upper bound it cannot reach"}
     roofline_detect = {"bound": "hbm", "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": det_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                       "frac": det_gbs / hbm_peak, "traffic": det_traffic, "peak_source": hbm_src,
                        "kernels": "detect_cm + thr + rowmask + scans + emit", "ms_per_launch": det_ms_avg,
                        "algorithmic_bytes_per_launch": det_bytes,
-                       "note": "ALU-bound (99-comparator 5x5 median per pixel), see DESIGN.md"}
+                       "note": "ALU-pipe bound: the packed-u16 median network keeps the ALU pipe 81 % busy (ncu, profiles/r01c_detect_packed_kernel.txt); DRAM traffic equals the algorithmic bytes"}
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
