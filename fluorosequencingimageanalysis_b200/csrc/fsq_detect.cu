@@ -60,6 +60,7 @@ static int64_t carve(DetectScratch* s, char* base, int F, int H, int W) {
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
     // scipy.ndimage mode='reflect' == numpy 'symmetric':  d c b a | a b c d | d c b a
+    if ((unsigned)i < (unsigned)n) return i;           // interior: no integer modulo
     if (n == 1) return 0;
     const int p = 2 * n;
     i %= p;
