@@ -33,6 +33,7 @@
 // loads and a handful of flops.
 #include "fsq_common.cuh"
 #include "fsq_median.cuh"
+#include "fsq_chol7.cuh"
 #include <string.h>
 
 namespace fsq {
@@ -215,56 +216,6 @@ __device__ __forceinline__ void w_sincos_deg(double th, double* sn, double* cs) 
     const double ss = swap ? c : s, cc = swap ? s : c;
     *sn = (q & 2) ? -ss : ss;
     *cs = ((q + 1) & 2) ? -cc : cc;
-}
-
-// -------------------------------------------------------------------------------------------
-// 7x7 Cholesky of the column-scaled, damped normal matrix
-//     M = As + par * T,   As = S^-1 A S^-1 (unit diagonal),  T = (D/S)^2
-// As read from shared memory ([entry][thread]); singular pivots are skipped (Li = 0).
-// -------------------------------------------------------------------------------------------
-template <int TPB>
-__device__ __forceinline__ unsigned w_chol7(const float* __restrict__ sA, const float (&T)[WNP],
-                                            float par, float (&L)[WNT], float (&Li)[WNP], float eps) {
-    unsigned ok = 0;
-#pragma unroll
-    for (int j = 0; j < WNP; ++j) {
-        float dj = fmaf(par, T[j], sA[wtri(j, j) * TPB]);
-#pragma unroll
-        for (int k = 0; k < j; ++k) dj = fmaf(-L[wtri(j, k)], L[wtri(j, k)], dj);
-        const bool good = dj > eps;
-        const float inv = good ? rsqrtf(dj) : 0.0f;
-        Li[j] = inv;
-        L[wtri(j, j)] = dj * inv;
-        ok |= (good ? 1u : 0u) << j;
-#pragma unroll
-        for (int i = j + 1; i < WNP; ++i) {
-            float sacc = sA[wtri(i, j) * TPB];
-#pragma unroll
-            for (int k = 0; k < j; ++k) sacc = fmaf(-L[wtri(i, k)], L[wtri(j, k)], sacc);
-            L[wtri(i, j)] = sacc * inv;
-        }
-    }
-    return ok;
-}
-
-__device__ __forceinline__ void w_fwd7(const float (&L)[WNT], const float (&Li)[WNP], const float (&rhs)[WNP], float (&z)[WNP]) {
-#pragma unroll
-    for (int j = 0; j < WNP; ++j) {
-        float s = rhs[j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) s = fmaf(-L[wtri(j, k)], z[k], s);
-        z[j] = s * Li[j];
-    }
-}
-
-__device__ __forceinline__ void w_bwd7(const float (&L)[WNT], const float (&Li)[WNP], float (&z)[WNP]) {
-#pragma unroll
-    for (int j = WNP - 1; j >= 0; --j) {
-        float s = z[j];
-#pragma unroll
-        for (int i = j + 1; i < WNP; ++i) s = fmaf(-L[wtri(i, j)], z[i], s);
-        z[j] = s * Li[j];
-    }
 }
 
 // One pass over the window at pt: chi^2 in FP64; J^T J (packed), J^T f in FP32 (J = d residual / dp).
@@ -593,17 +544,18 @@ lmwarp_kernel(const WarpArgs a) {
                 // parked
             } else if (status == 0) {
                 // ---------------------------------------------------------- lmpar (:2077-2190), FP32
-                float L[WNT], Li[WNP], rhs[WNP], z[WNP], T[WNP], pf[WNP];
+                Chol7 ch;
+                float rhs[WNP], z[WNP], T[WNP], pf[WNP];
 #pragma unroll
                 for (int i = 0; i < WNP; ++i) { rhs[i] = -sg[i * TPB]; const float t = diag[i] * iS[i]; T[i] = t * t; }
                 float prr = 0.0f, par_used = 0.0f, fp = 0.0f, parl = 0.0f, paru = 0.0f, dxnorm = 0.0f;
                 unsigned ok = 0;
 #pragma unroll 1
                 for (int it = 0; it <= WLMPAR_MAX; ++it) {
-                    const unsigned okk = w_chol7<TPB>(sA, T, prr, L, Li, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f);
+                    const unsigned okk = chol7_factor<TPB>(sA, T, prr, it == 0 ? 16.0f * 1.1920929e-07f : 0.0f, ch);
                     if (it == 0) ok = okk;
-                    w_fwd7(L, Li, rhs, z);
-                    w_bwd7(L, Li, z);
+                    chol7_fwd(ch, rhs, z);
+                    chol7_bwd(ch, z);
                     float dx2 = 0.0f;
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) { pf[j] = z[j] * iS[j]; const float t = diag[j] * pf[j]; dx2 = fmaf(t, t, dx2); }
@@ -621,7 +573,7 @@ lmwarp_kernel(const WarpArgs a) {
                     const float idn = __fdividef(1.0f, dxnorm);
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) u[j] = T[j] * z[j] * idn;          // D^2 p / |D p| in scaled variables
-                    w_fwd7(L, Li, u, w);
+                    chol7_fwd(ch, u, w);
                     float t2 = 0.0f;
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) t2 = fmaf(w[j], w[j], t2);
