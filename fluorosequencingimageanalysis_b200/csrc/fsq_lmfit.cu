@@ -1089,6 +1089,10 @@ extern "C" int fsq_fit_candidates(const void* frames, int dtype_code, int n_fram
         set_error("fsq_fit_candidates: unsupported frame dtype code %d", dtype_code);
         return FSQ_E_ARG;
     }
+    if (opts->solver == FSQ_SOLVER_FAST && (H > 65535 || W > 65535)) {
+        set_error("fsq_fit_candidates: frames larger than 65535 pixels per side are not supported by FSQ_SOLVER_FAST");
+        return FSQ_E_ARG;
+    }
     if (opts->solver == FSQ_SOLVER_FAST)
         return warp_fit_candidates(frames, dtype_code, H, W, cand_hw, cand_frame, n, (const long long*)n_dev, opts, out_fit,
                                    out_int, fit_img, scratch, (cudaStream_t)stream);

@@ -63,9 +63,21 @@ struct WarpArgs {
     unsigned long long* work_counter;        // queue head of the running launch
     unsigned long long* strag_count;         // number of parked fits (phase 1 appends, phase 2 consumes)
     struct StragRec* strag;                  // parked fit states
+    struct PrepRec* prep;                    // per-candidate start records
     int cap;                                 // phase 1: park a fit after this many passes (0 = never)
     int resume;                              // phase 2: the work list is strag[0 .. *strag_count)
 };
+
+// Everything the LM kernel needs to start one candidate, written by fit_prep_kernel: a refill is eight
+// 16-byte loads from one 128-byte line instead of two dependent round trips (candidate list, then 25
+// scattered pixels) -- the refill was 10 % of the kernel's time with 2 lanes of every warp refilling per tick.
+struct __align__(16) PrepRec {
+    int px[25];                  // the 5x5 raw window, raster order
+    int med, max, sum;           // numpy.median / max / sum of the window (pflib.py:199-205)
+    unsigned hw;                 // candidate pixel: h << 16 | w
+    double sst;                  // total sum of squares around the window mean (r_2, pflib.py:464)
+};
+static_assert(sizeof(PrepRec) == 128, "PrepRec must be 128 bytes");
 
 // State of a fit parked by phase 1 (everything the LM iteration carries from one accepted point
 // to the next; the normal equations are re-formed from x by the resuming launch, bit for bit).
@@ -153,11 +165,20 @@ fit_prep_kernel(const WarpArgs a) {
         if (r == 0 || r == 4 || c == 0 || c == 4) { const double e3 = (double)v[q] - emean; evar += e3 * e3; }
     }
     const int imed = median25<int>(v);                           // numpy.median of 25 (pflib.py:199)
-    int* oi = a.out_int + i * 4;
-    oi[0] = imed; oi[1] = imax; oi[2] = (int)isum; oi[3] = 0;
-    double* o = a.out_fit + i * 12;
-    o[8] = sst;
-    o[9] = ((double)imax - emean) / sqrt(evar / 16.0);           // illumina_s_n, pflib.py:261-281
+    // (v[] is permuted by the selection network: re-read the window for the record)
+    PrepRec rec;
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) rec.px[r * 5 + c] = w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
+    rec.med = imed; rec.max = imax; rec.sum = (int)isum;
+    rec.hw = ((unsigned)ch << 16) | (unsigned)cw;
+    rec.sst = sst;
+    uint4* dst = reinterpret_cast<uint4*>(a.prep + i);
+    const uint4* src = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = src[q];
+    a.out_fit[i * 12 + 9] = ((double)imax - emean) / sqrt(evar / 16.0);   // illumina_s_n, pflib.py:261-281 (final)
 }
 
 // -------------------------------------------------------------------------------------------
@@ -337,6 +358,7 @@ lmwarp_kernel(const WarpArgs a) {
     bool nonfinite = false;
     double x[WNP], y[WNP];
     double ss0 = -1.0, ss1 = -1.0;                      // chi^2 at x, chi^2 of the last trial point
+    double sst = 0.0;                                   // total sum of squares of the window (pflib path)
     Lim<PFLIB> lim;
     lim.lo1 = 0.0; lim.lo = nullptr; lim.hi = nullptr; lim.qll = PF_QLL; lim.qul = PF_QUL;
     float delta = 0.0f, par = 0.0f, xnorm = 0.0f, gnorm = 0.0f, pnorm = 0.0f, prered = 0.0f, dirder = 0.0f, rss0 = 0.0f;
@@ -359,14 +381,19 @@ lmwarp_kernel(const WarpArgs a) {
                 else {
                     idx = a.resume ? a.strag[slot].idx : slot;
                     if (PFLIB) {
-                        cand_h = a.cand_hw[2 * idx]; cand_w = a.cand_hw[2 * idx + 1];
-                        const size_t fbase = (size_t)a.cand_frame[idx] * a.H * a.W + (size_t)(cand_h - 2) * a.W + (cand_w - 2);
-#pragma unroll 1
-                        for (int r = 0; r < WIN; ++r)
+                        uint4 q[8];                                   // one 128-byte start record
+                        {
+                            const uint4* src = reinterpret_cast<const uint4*>(a.prep + idx);
 #pragma unroll
-                            for (int c = 0; c < WIN; ++c)
-                                sd[(r * WIN + c) * TPB] = (double)w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
-                        const int4 pre = *reinterpret_cast<const int4*>(a.out_int + idx * 4);
+                            for (int k = 0; k < 8; ++k) q[k] = src[k];
+                        }
+#define WREC(i) ((i) % 4 == 0 ? q[(i) / 4].x : (i) % 4 == 1 ? q[(i) / 4].y : (i) % 4 == 2 ? q[(i) / 4].z : q[(i) / 4].w)
+#pragma unroll
+                        for (int k = 0; k < P; ++k) sd[k * TPB] = (double)(int)WREC(k);
+                        cand_h = (int)(WREC(28) >> 16); cand_w = (int)(WREC(28) & 0xffffu);
+                        sst = __hiloint2double((int)WREC(31), (int)WREC(30));
+                        const int4 pre = make_int4((int)WREC(25), (int)WREC(26), (int)WREC(27), 0);
+#undef WREC
                         const double dmax = (double)pre.y, dmean = (double)pre.z / 25.0;
                         lim.lo1 = (dmax - dmean) / 3.0;                                    // pflib.py:205
                         x[0] = (double)pre.x; x[1] = dmax; x[2] = 2.5; x[3] = 2.5; x[4] = 1.0; x[5] = 1.0; x[6] = 0.0;
@@ -677,7 +704,6 @@ lmwarp_kernel(const WarpArgs a) {
                 if (status > 0) ++nfev;                                                  // :1351-1355
                 if (PFLIB) {
                     double* o = a.out_fit + idx * 12;
-                    const double sst = o[8];
                     o[0] = (x[2] + (double)cand_h) - 2.5;                                // pflib.py:461
                     o[1] = (x[3] + (double)cand_w) - 2.5;
                     o[2] = x[0]; o[3] = x[1]; o[4] = x[4]; o[5] = x[5]; o[6] = x[6];
@@ -742,7 +768,8 @@ fit_image_generic_kernel(const double* __restrict__ params, const int32_t* __res
     }
 }
 
-long long warp_scratch_bytes(long long n) { return 64 + (long long)sizeof(StragRec) * (n > 0 ? n : 0); }
+// [64 B header | n start records | n parked-fit records]
+long long warp_scratch_bytes(long long n) { return 64 + (long long)(sizeof(PrepRec) + sizeof(StragRec)) * (n > 0 ? n : 0); }
 
 // Persistent launch(es) of one kernel flavour: phase 1 over every fit (parked after `park_after`
 // passes when that is set), phase 2 over the parked fits.
@@ -795,7 +822,9 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     a.frames = frames; a.fdtype = dtype_code; a.H = H; a.W = W; a.cand_hw = cand_hw; a.cand_frame = cand_frame;
     a.n = n; a.n_dev = n_dev; a.o = *opts; a.out_fit = out_fit; a.out_int = out_int; a.fit_img = fit_img;
     unsigned long long* head = (unsigned long long*)scratch;          // [0] queue head, [1] parked count
-    a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);
+    a.work_counter = head; a.strag_count = head + 1;
+    a.prep = (PrepRec*)((char*)scratch + 64);
+    a.strag = (StragRec*)((char*)scratch + 64 + sizeof(PrepRec) * (size_t)n);
     const unsigned flat = (unsigned)((n + 127) / 128);
     FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     fit_prep_kernel<<<flat, 128, 0, st>>>(a);
@@ -823,7 +852,7 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     // when parking is requested, the parked states
     fsq_lm_opts o = *opts;
     void* scratch = nullptr;
-    const size_t bytes = (size_t)(o.park_after > 0 ? warp_scratch_bytes(n) : 64);
+    const size_t bytes = (size_t)(o.park_after > 0 ? 64 + sizeof(StragRec) * (size_t)n : 64);
     FSQ_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
     unsigned long long* head = (unsigned long long*)scratch;
     a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);

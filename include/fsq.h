@@ -172,8 +172,8 @@ int fsq_gaussfit_batch_trace(const void* windows, int dtype_code, int64_t n, int
  *              pflib.py:461), rmse, r_2, s_n, chi2, (reserved)
  *  out_int     [n, 4] int32: status, niter, nfev, n_qrsolv
  *  fit_img     [n, 25] float64 or NULL
- *  scratch     device scratch of at least fsq_fit_scratch_bytes(n) bytes (work-queue head +
- *              the states of parked fits); the call initialises it
+ *  scratch     device scratch of at least fsq_fit_scratch_bytes(n) bytes (work-queue head, one
+ *              128-byte start record per candidate, the states of parked fits); the call initialises it
  * ------------------------------------------------------------------------------------------ */
 int fsq_fit_candidates(const void* frames, int dtype_code, int n_frames, int H, int W,
                        const int32_t* cand_hw, const int32_t* cand_frame, int64_t n,

@@ -86,7 +86,7 @@ def test_argument_validation_without_gpu():
     assert L.fsq_fit_candidates(one, _lib.FSQ_U16, 1, 8, 8, one, one, 0, null, ctypes.byref(o), one, one,
                                 null, one, 64, null) == 0
     # scratch smaller than fsq_fit_scratch_bytes(n) is refused before anything is launched
-    assert L.fsq_fit_scratch_bytes(0) == 64 and L.fsq_fit_scratch_bytes(1000) == 64 + 128 * 1000
+    assert L.fsq_fit_scratch_bytes(0) == 64 and L.fsq_fit_scratch_bytes(1000) == 64 + 256 * 1000
     rc = L.fsq_fit_candidates(one, _lib.FSQ_U16, 1, 8, 8, one, one, 10, null, ctypes.byref(o), one, one,
                               null, one, 64, null)
     assert rc == _lib.FSQ_E_CAPACITY and "scratch" in _lib.last_error()
