@@ -497,7 +497,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="fast", choices=["fast", "fast64", "minpack-faithful", "minpack-clean"])
-    ap.add_argument("--depth", type=int, default=5, help="batches in flight (streams) in the pipelined regions")
+    ap.add_argument("--depth", type=int, default=6, help="batches in flight (streams) in the pipelined regions")
     ap.add_argument("--no-parity-solver", action="store_true")
     ap.add_argument("--park", type=int, default=None, help="fsq_lm_opts.park_after override (scheduling only)")
     ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
