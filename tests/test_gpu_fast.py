@@ -267,3 +267,51 @@ def test_fast_generic_edge_cases():
     # a window size the FAST solver does not take is refused, not silently re-routed
     with pytest.raises(ValueError):
         engine.gaussfit_batch(np.zeros((1, 7, 7)), p0[:1], lo[:1], hi[:1], lmin[:1], lmax[:1], solver="fast")
+
+
+# ------------------------------------------------------------------------------------ BASELINE configs 3 / 4 shapes
+def test_config4_dense_2048_frame_properties():
+    """BASELINE configs[3]: one 2048x2048 frame at high density (20 000 spots, overlaps present).  The CPU
+    oracle detects the full frame (bit-exact list); fits are checked through size-independent properties:
+    the FAST solver against the all-FP64 solver on a sample, every fit ends with a convergence status, and
+    the same frame inside a 2-frame batch returns the same bits."""
+    engine, _, synth, _ = _mods()
+    img = synth.synth_frame(4, H=2048, W=2048, n_spots=20000)
+    want = np.array(po.psf_candidates(img), dtype=np.int32).reshape(-1, 2)
+    res = engine.find_peptides_batch(img, solver="fast", faithful=False)
+    assert np.array_equal(res.cand_hw, want)
+    assert len(want) > 150000
+    assert (res.ints[:, 0] > 0).all() and np.isfinite(res.fit[:, :11]).all()
+    import torch
+    pick = np.sort(np.random.default_rng(0).choice(len(want), 20000, replace=False))
+    hw = torch.as_tensor(want[pick]).cuda().contiguous()
+    fr = torch.zeros(len(pick), dtype=torch.int32, device="cuda")
+    f64, i64, _ = engine.fit_candidates(img, hw, fr, len(pick), solver="fast64", faithful=False)
+    a = res.fit[pick][:, [2, 3, 0, 1, 4, 5, 6]].copy()
+    b = f64.cpu().numpy()[:, [2, 3, 0, 1, 4, 5, 6]].copy()
+    ok = agree(a, b)
+    print("config-4 frame: %d candidates; fast vs fast64 on 20000 of them: %.4f" % (len(want), ok.mean()))
+    assert ok.mean() > 0.98
+    two = engine.find_peptides_batch(np.stack([img, img]), solver="fast", faithful=False)
+    n0 = int(two.n_cand[0])
+    assert n0 == len(want) == int(two.n_cand[1])
+    assert np.array_equal(two.fit[:n0].view(np.int64), res.fit.view(np.int64))
+    assert np.array_equal(two.fit[n0:2 * n0].view(np.int64), res.fit.view(np.int64))
+
+
+def test_config3_experiment_stack_is_frame_independent():
+    """BASELINE configs[2] shape (cycles x fields of one experiment, 1000 spots per field): a (cycle, field)
+    stack through one batch equals every frame fitted on its own."""
+    engine, _, synth, _ = _mods()
+    frames = np.stack([synth.synth_frame(300 + k, H=512, W=512, n_spots=1000) for k in range(4)])
+    batch = engine.find_peptides_batch(frames, solver="fast", faithful=False)
+    off = 0
+    for k in range(len(frames)):
+        one = engine.find_peptides_batch(frames[k], solver="fast", faithful=False)
+        n = int(batch.n_cand[k])
+        assert n == len(one.cand_hw) and n > 8000
+        assert np.array_equal(batch.cand_hw[off:off + n], one.cand_hw)
+        assert np.array_equal(batch.fit[off:off + n].view(np.int64), one.fit.view(np.int64))
+        assert (batch.cand_frame[off:off + n] == k).all()
+        off += n
+    assert off == int(batch.n_cand[-1])
