@@ -250,7 +250,11 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
     // per-column terms of the rotated offsets (numpy.indices: y = column index pairs with p[2]);
     // 5x5: tables in registers; larger windows: one multiply-add per pixel instead
+#ifdef WPASS_ROLLED
+    constexpr bool TABLES = false;
+#else
     constexpr bool TABLES = (WIN <= 5);
+#endif
     double ca[TABLES ? WIN : 1], cb[TABLES ? WIN : 1];
     float caf[TABLES ? WIN : 1], cbf[TABLES ? WIN : 1];
     if (TABLES) {
@@ -281,7 +285,11 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
         const float raf = (float)ra, rbf = (float)rb;
         const double* drow = sd + r * WIN * TPB;
         dx -= 1.0;
+#ifdef WPASS_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int c = 0; c < WIN; ++c) {
             double av, bv;
             float af, bf;
