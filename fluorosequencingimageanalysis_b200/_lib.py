@@ -19,7 +19,7 @@ FSQ_OK, FSQ_E_ARG, FSQ_E_CAPACITY, FSQ_E_CUDA, FSQ_E_RANGE = 0, -1, -2, -3, -4
 EXPORTED = ["fsq_version", "fsq_last_error", "fsq_detect_scratch_bytes", "fsq_detect",
             "fsq_detect_flags", "fsq_detect_copy_cm32", "fsq_lm_default_opts",
             "fsq_gaussfit_batch", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
-            "fsq_metrics", "fsq_photometry",
+            "fsq_metrics", "fsq_photometry", "fsq_moments",
             "fsq_fma_peak"]
 
 
@@ -79,6 +79,8 @@ def load():
     L.fsq_metrics.argtypes = [vp, vp, i64, vp, vp]
     L.fsq_photometry.restype = i32
     L.fsq_photometry.argtypes = [vp, i32, i32, i32, i32, vp, vp, i64, i32, i32, i32, vp, vp]
+    L.fsq_moments.restype = i32
+    L.fsq_moments.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp]
     L.fsq_fma_peak.restype = i32
     L.fsq_fma_peak.argtypes = [i32, _c.POINTER(dbl), vp]
     _LIB = L

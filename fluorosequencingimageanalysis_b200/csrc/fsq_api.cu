@@ -139,6 +139,130 @@ photometry_kernel(const void* __restrict__ frames, int dtype, int H, int W,
     if (lane == 0) out[i] = res;
 }
 
+
+// ---- start values from image moments (agpy/gaussfitter.py:29-61), one warp per window -------------
+//  out[i] = (height, amplitude, x, y, width_x, width_y, 0): height = median of the window, amplitude =
+//  max - height, y / x = first argmax of the |data|-weighted marginal first moments (divided by
+//  sum|data|, gaussfitter.py:39-40), widths = sqrt(sum|(k - centre) * line| / sum|line|) along the row /
+//  column through that argmax ("FIRST moment, not second", :42-46).  Every sum runs in the order numpy's
+//  add.reduce uses (8 strided accumulators + sequential remainder for a contiguous 1-D run of >= 8
+//  elements, plain sequential otherwise and across rows for axis=0), with explicit _rn intrinsics so
+//  that no product is contracted into an FMA: float64 windows give the reference's bits.
+constexpr int MO_MAXW = 11;
+template <class F>
+__device__ __forceinline__ double np_sum(int n, F f) {         // numpy pairwise_sum for n < 128
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, f(i));
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f(j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, f(i));
+    return res;
+}
+
+__global__ void __launch_bounds__(128)
+moments_kernel(const void* __restrict__ windows, int dtype, long long n, int win, double* out,
+               const double* __restrict__ lo, const double* __restrict__ hi,
+               const uint8_t* __restrict__ lim_lo, const uint8_t* __restrict__ lim_hi) {
+    __shared__ double px[4][MO_MAXW * MO_MAXW];
+    __shared__ double marg[4][2 * MO_MAXW + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const int P = win * win;
+    double* d = px[warp];
+    double vmax = -1.0 / 0.0;
+    bool has_nan = false;
+    for (int q = lane; q < P; q += 32) {
+        double v;
+        const size_t off = (size_t)i * P + q;
+        switch (dtype) {
+            case FSQ_U8:  v = (double)((const uint8_t*)windows)[off]; break;
+            case FSQ_U16: v = (double)((const uint16_t*)windows)[off]; break;
+            case FSQ_I16: v = (double)((const int16_t*)windows)[off]; break;
+            case FSQ_I32: v = (double)((const int32_t*)windows)[off]; break;
+            case FSQ_I64: v = (double)((const long long*)windows)[off]; break;
+            default:      v = ((const double*)windows)[off]; break;
+        }
+        d[q] = v;
+        vmax = fmax(vmax, v);                      // (numpy's max propagates NaN; handled through has_nan)
+        has_nan |= (v != v);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, m));
+    has_nan = __any_sync(0xffffffffu, has_nan);
+    __syncwarp();
+    // lanes 0..win-1: row marginals (sum over the contiguous axis 1 -> pairwise order); lanes 16..: column
+    // marginals (axis 0 -> row after row); lane 15: total = sum|data| over the flat window
+    if (lane < win) {
+        marg[warp][lane] = np_sum(win, [&](int c) { return __dmul_rn((double)c, fabs(d[lane * win + c])); });
+    } else if (lane >= 16 && lane - 16 < win) {
+        const int c = lane - 16;
+        double s = 0.0;
+        for (int r = 0; r < win; ++r) s = __dadd_rn(s, __dmul_rn((double)r, fabs(d[r * win + c])));
+        marg[warp][MO_MAXW + c] = s;
+    } else if (lane == 15) {
+        marg[warp][2 * MO_MAXW] = np_sum(P, [&](int q) { return fabs(d[q]); });
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double total = marg[warp][2 * MO_MAXW];
+        int ya = 0, xa = 0;                         // first maximum, like numpy.argmax (NaN wins there too)
+        double by = __ddiv_rn(marg[warp][0], total), bx = __ddiv_rn(marg[warp][MO_MAXW], total);
+        for (int k = 1; k < win; ++k) {
+            const double qy = __ddiv_rn(marg[warp][k], total), qx = __ddiv_rn(marg[warp][MO_MAXW + k], total);
+            if (qy > by) { by = qy; ya = k; }
+            if (qx > bx) { bx = qx; xa = k; }
+        }
+        // gaussfitter.py:41-45: the *row* through y is paired with (k - y), the *column* through x with (k - x)
+        const double wx = sqrt(__ddiv_rn(
+            np_sum(win, [&](int k) { return fabs(__dmul_rn((double)(k - ya), d[ya * win + k])); }),
+            np_sum(win, [&](int k) { return fabs(d[ya * win + k]); })));
+        const double wy = sqrt(__ddiv_rn(
+            np_sum(win, [&](int k) { return fabs(__dmul_rn((double)(k - xa), d[k * win + xa])); }),
+            np_sum(win, [&](int k) { return fabs(d[k * win + xa]); })));
+        double* o = out + i * 7;
+        o[2] = (double)xa; o[3] = (double)ya; o[4] = wx; o[5] = wy; o[6] = 0.0;
+    }
+    // median by rank counting (numpy.median: mean of the two middle elements for an even count)
+    const int k_lo = (P - 1) / 2, k_hi = P / 2;
+    double pick = 0.0;
+    for (int a = lane; a < P; a += 32) {
+        const double va = d[a];
+        int c = 0;
+        for (int b = 0; b < P; ++b) { const double vb = d[b]; c += (vb < va) || (vb == va && b < a); }
+        if (c == k_lo) pick += va;
+        if (c == k_hi) pick += va;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) pick += __shfl_xor_sync(0xffffffffu, pick, m);
+    if (lane == 0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        const double med = has_nan ? nan : 0.5 * pick;
+        out[i * 7 + 0] = med;
+        out[i * 7 + 1] = (has_nan ? nan : vmax) - med;
+    }
+    if (lo) {                                       // gaussfitter.py:202-204: start values clipped into the limits
+        __syncwarp();
+        if (lane < 7) {
+            double v = out[i * 7 + lane];
+            if (lim_hi[lane] && v > hi[lane]) v = hi[lane];
+            if (lim_lo[lane] && v < lo[lane]) v = lo[lane];
+            out[i * 7 + lane] = v;
+        }
+    }
+}
+
 // ---- FMA-pipe micro-benchmark (roofline denominator of bench.py) -------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
@@ -219,5 +343,19 @@ extern "C" int fsq_fma_peak(int fp64, double* flops_out_host, void* stream) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
     const double flop = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
     *flops_out_host = flop / (double(best) * 1e-3);
+    return FSQ_OK;
+}
+
+extern "C" int fsq_moments(const void* windows, int dtype_code, int64_t n, int win, const double* lo, const double* hi,
+                           const uint8_t* lim_lo, const uint8_t* lim_hi, double* p0_out, void* stream) {
+    if (n < 0) { set_error("fsq_moments: n < 0"); return FSQ_E_ARG; }
+    if (n == 0) return FSQ_OK;
+    if (!windows || !p0_out) { set_error("fsq_moments: NULL pointer argument"); return FSQ_E_ARG; }
+    if (win < 1 || win > MO_MAXW) { set_error("fsq_moments: window side must be in 1..%d (got %d)", MO_MAXW, win); return FSQ_E_ARG; }
+    if (dtype_code < FSQ_U8 || dtype_code > FSQ_I64) { set_error("fsq_moments: unsupported dtype code %d", dtype_code); return FSQ_E_ARG; }
+    if (lo && !(hi && lim_lo && lim_hi)) { set_error("fsq_moments: lo, hi, lim_lo, lim_hi go together"); return FSQ_E_ARG; }
+    moments_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(windows, dtype_code, n, win, p0_out,
+                                                                             lo, hi, lim_lo, lim_hi);
+    FSQ_LAUNCH_CHECK();
     return FSQ_OK;
 }

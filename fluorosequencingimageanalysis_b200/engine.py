@@ -259,6 +259,62 @@ def gaussfit_batch_trace(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, tra
     return r, trace.cpu().numpy()
 
 
+def _device_windows(windows, dev):
+    """numpy / torch windows -> contiguous CUDA tensor [n,win,win], int64 for integer pixels, float64 otherwise"""
+    if isinstance(windows, np.ndarray):
+        a = windows
+        kind = np.int64 if a.dtype.kind in "iub" else np.float64
+        w = torch.from_numpy(np.ascontiguousarray(a.astype(kind))).to(dev)
+    else:
+        w = windows.to(dev).contiguous()
+        if w.dtype not in (torch.float64, torch.int64):
+            w = w.to(torch.float64 if w.dtype.is_floating_point else torch.int64)
+    if w.dim() == 2:
+        w = w.unsqueeze(0)
+    if w.dim() != 3 or w.shape[1] != w.shape[2]:
+        raise ValueError("windows must be square")
+    return w
+
+
+def moments_batch(windows, lo=None, hi=None, lim_lo=None, lim_hi=None):
+    """gaussfitter.moments (agpy/gaussfitter.py:29-61; circle=0, rotate=1, vheight=1, median estimator) for
+    n windows [n,win,win] -> device tensor [n,7] (height, amplitude, x, y, width_x, width_y, 0); with the
+    four limit vectors [7] the values are clipped into the limits like gaussfitter.py:202-204."""
+    L = _lib.load()
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    w = _device_windows(windows, dev)
+    n, win, _ = w.shape
+    out = torch.empty((n, 7), dtype=torch.float64, device=dev)
+    lims = [None] * 4
+    if lo is not None:
+        lims = [torch.as_tensor(np.asarray(v), dtype=dt).to(dev).reshape(7).contiguous()
+                for v, dt in ((lo, torch.float64), (hi, torch.float64), (lim_lo, torch.uint8), (lim_hi, torch.uint8))]
+    _lib.check(L.fsq_moments(_ptr(w), _TORCH_DTYPE_CODE[w.dtype], n, win, _ptr(lims[0]), _ptr(lims[1]),
+                             _ptr(lims[2]), _ptr(lims[3]), _ptr(out), _stream()))
+    return out
+
+
+GAUSSFIT_DEFAULT_LIMITS = (np.zeros(7), np.array([0, 0, 0, 0, 0, 0, 360.]),                  # gaussfitter.py:143-146
+                           np.array([0, 0, 0, 0, 1, 1, 1], dtype=np.uint8), np.array([0, 0, 0, 0, 0, 0, 1], dtype=np.uint8))
+
+
+def gaussfit_default_batch(windows, solver="fast", faithful=True, **kw):
+    """``gaussfit(data)`` with its default arguments (moments start, widths and angle bounded below, angle
+    <= 360; agpy/gaussfitter.py:142-148, 188-204) for n windows, start values and fits all on the device --
+    the BASELINE configs[0] / configs[3] "11x11 subimages" workload.  -> (FitBatch, p0 [n,7] device)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    require_cuda()
+    w = _device_windows(windows, dev)
+    n = w.shape[0]
+    lo, hi, lmin, lmax = GAUSSFIT_DEFAULT_LIMITS
+    p0 = moments_batch(w, lo, hi, lmin, lmax)
+    ex = lambda v, dt: torch.as_tensor(v, dtype=dt).to(dev).expand(n, 7).contiguous()
+    r = gaussfit_batch(w, p0, ex(lo, torch.float64), ex(hi, torch.float64), ex(lmin, torch.uint8), ex(lmax, torch.uint8),
+                       faithful=faithful, solver=solver, **kw)
+    return r, p0
+
+
 def metrics_batch(sub, fit):
     """pflib.py:463-473 for n (sub_img, fit_img) pairs -> [n,3] (r_2, rmse, s_n)."""
     L = _lib.load()

@@ -15,31 +15,22 @@ from . import engine
 
 
 def moments(data, circle, rotate, vheight, estimator=median, **kwargs):
-    """agpy/gaussfitter.py:29-61: (height, amplitude, x, y, width_x, width_y, rotation)
-    start values from moments; host-side argument marshalling."""
-    total = np.abs(data).sum()
-    Y, X = np.indices(data.shape)
-    y = np.argmax((X * np.abs(data)).sum(axis=1) / total)
-    x = np.argmax((Y * np.abs(data)).sum(axis=0) / total)
-    col = data[int(y), :]
-    width_x = np.sqrt(np.abs((np.arange(col.size) - y) * col).sum() / np.abs(col).sum())
-    row = data[:, int(x)]
-    width_y = np.sqrt(np.abs((np.arange(row.size) - x) * row).sum() / np.abs(row).sum())
-    width = (width_x + width_y) / 2.
-    height = estimator(data.ravel())
-    amplitude = data.max() - height
-    mylist = [amplitude, x, y]
-    if np.isnan(width_y) or np.isnan(width_x) or np.isnan(height) or np.isnan(amplitude):
+    """agpy/gaussfitter.py:29-61 -> [height,] amplitude, x, y, width_x, width_y[, 0.] (or one mean
+    width for circle=1).  The statistics come from the device kernel behind ``fsq_moments``; a
+    non-default ``estimator`` (e.g. numpy.ma.median) replaces the height only, as in the reference."""
+    data = np.asarray(data)
+    m = engine.moments_batch(data[None])[0].cpu().numpy()
+    height, amplitude, x, y, width_x, width_y = (float(v) for v in m[:6])
+    if estimator is not median:
+        height = estimator(data.ravel())
+        amplitude = data.max() - height
+    if any(np.isnan(v) for v in (width_y, width_x, height, amplitude)):
         raise ValueError("something is nan")
-    if vheight == 1:
-        mylist = [height] + mylist
-    if circle == 0:
-        mylist = mylist + [width_x, width_y]
-        if rotate == 1:
-            mylist = mylist + [0.]
-    else:
-        mylist = mylist + [width]
-    return mylist
+    head = [height] if vheight == 1 else []
+    if circle != 0:
+        return head + [amplitude, int(x), int(y), (width_x + width_y) / 2.]
+    tail = [0.] if rotate == 1 else []
+    return head + [amplitude, int(x), int(y), width_x, width_y] + tail
 
 
 def twodgaussian(inpars, circle=False, rotate=True, vheight=True, shape=None):
@@ -115,13 +106,13 @@ def gaussfit(data, err=None, params=(), autoderiv=True, return_all=False, circle
     data = np.asarray(data)
     usemoment = np.array(usemoment, dtype='bool')
     params = np.array(params, dtype='float')
+    if autoderiv == 0:
+        raise ValueError("I'm sorry, I haven't implemented this feature yet.")   # gaussfitter.py:239
     if usemoment.any() and len(params) == len(usemoment):
         moment = np.array(moments(data, circle, rotate, vheight, **kwargs), dtype='float')
         params[usemoment] = moment[usemoment]
     elif len(params) == 0:
         params = np.array(moments(data, circle, rotate, vheight, **kwargs), dtype='float')
-    if autoderiv == 0:
-        raise ValueError("I'm sorry, I haven't implemented this feature yet.")   # gaussfitter.py:239
     if circle or not rotate or not vheight or err is not None or np.any(np.asarray(fixed)):
         raise NotImplementedError("the CUDA path fits the 7-parameter model (circle=0, rotate=1, "
                                   "vheight=1, err=None, no fixed parameters) -- SURVEY.md 8(b)")

@@ -183,6 +183,19 @@ int fsq_fit_candidates(const void* frames, int dtype_code, int n_frames, int H, 
 
 int64_t fsq_fit_scratch_bytes(int64_t n);
 
+/* ------------------------------------------------------------------------------------------
+ * Start values from image moments -- replaces gaussfitter.moments (agpy/gaussfitter.py:29-61) with
+ * circle = 0, rotate = 1, vheight = 1 and the default median estimator, for a batch of windows:
+ *  p0_out [n, 7] = (height = median, amplitude = max - height, x, y, width_x, width_y, 0).
+ * A window holding a NaN gives NaN height / amplitude (the Python mirror raises the reference's
+ * ValueError("something is nan")).  windows [n, win, win] of any FSQ_* dtype, win <= 11.  Sums run
+ * in numpy's add.reduce order, so float64 windows reproduce the reference's start values bit for bit.
+ * lo / hi / lim_lo / lim_hi [7] (device, all four or all NULL): clip the start values into the
+ * limits as gaussfit does before calling mpfit (gaussfitter.py:202-204).
+ * ------------------------------------------------------------------------------------------ */
+int fsq_moments(const void* windows, int dtype_code, int64_t n, int win, const double* lo, const double* hi,
+                const uint8_t* lim_lo, const uint8_t* lim_hi, double* p0_out, void* stream);
+
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);

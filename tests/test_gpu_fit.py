@@ -339,3 +339,36 @@ def test_config1_final_psf_list_overlap(gpu_fits5, fits5):
     print("final PSFs: ref %d ours %d exact-key overlap %d, ref PSFs with ours within 1.5 px: %.3f" % (
         len(want), len(got), len(want & got), (d <= 1.5).mean()))
     assert (d <= 1.5).mean() >= 0.95
+
+
+# ------------------------------------------------------------------------------------ moments
+def test_device_moments_reproduce_reference_start_values():
+    """gaussfitter.moments (agpy/gaussfitter.py:29-61) on the device: bit-identical to the reference-generated
+    start values of the 11x11 golden (float64 windows -> numpy's summation order matters) and to the oracle on
+    random windows of every side 3..11, integer and float, including ties and negative pixels."""
+    engine, _, gaussfitter, _ = _mods()
+    g = golden("fits11_seed0.npz")
+    got = engine.moments_batch(g["windows"]).cpu().numpy()
+    assert np.array_equal(got, g["p0"])
+    assert np.array_equal(np.array(gaussfitter.moments(g["windows"][5], 0, 1, 1), dtype=float), g["p0"][5])
+    m = gaussfitter.moments(g["windows"][5], 1, 1, 1)                       # circle: one mean width
+    assert len(m) == 5 and m[4] == (g["p0"][5][4] + g["p0"][5][5]) / 2.
+    assert len(gaussfitter.moments(g["windows"][5], 0, 0, 0)) == 5          # no height, no angle
+    rng = np.random.default_rng(11)
+    for win in range(3, 12):
+        fl = rng.normal(100., 60., (40, win, win))
+        it = rng.integers(0, 6, (40, win, win)).astype(np.int64) * 100      # many ties
+        for batch in (fl, it, it.astype(np.uint16)):
+            got = engine.moments_batch(batch).cpu().numpy()
+            want = np.array([po.moments(b) for b in batch], dtype=float)
+            assert np.array_equal(got, want), (win, batch.dtype)
+    with pytest.raises(ValueError):
+        gaussfitter.moments(np.full((5, 5), np.nan), 0, 1, 1)               # gaussfitter.py:49-50
+    # default-argument gaussfit, start values and fits on the device, equals the host-marshalled call
+    r, p0 = engine.gaussfit_default_batch(g["windows"][:64], solver="minpack")
+    assert np.array_equal(p0.cpu().numpy(), g["p0"][:64])                   # none of these starts is clipped
+    p = gaussfitter.gaussfit(g["windows"][3])
+    assert np.array_equal(p, r.params[3].cpu().numpy())
+    lo, hi, lmin, lmax = engine.GAUSSFIT_DEFAULT_LIMITS
+    clipped = engine.moments_batch(-np.abs(fl), lo + 5.0, hi, np.ones(7, np.uint8), lmax).cpu().numpy()
+    assert (clipped >= 5.0).all()
