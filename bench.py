@@ -270,6 +270,8 @@ def run_ours(args):
     if args.park is not None:
         kw["park_after"] = args.park
     kw["warps_per_sm"] = args.warps_per_sm
+    if args.fetch == "psfs":
+        kw["consolidate"] = True          # the tail of find_peptides runs on the device in both timed regions
     cur = torch.cuda.current_stream()
 
     # ---- timed region A: inputs resident in HBM; K steps software-pipelined over `depth` streams
@@ -340,7 +342,7 @@ def run_ours(args):
 
     # ---- timed region B (e2e): pinned host frames in, packed results back on the host, every step;
     #      submit(k) / begin_fetch(k-1) / end_fetch(k-2) keeps H2D, kernels and D2H of neighbouring steps in flight
-    fe = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=True, **kw)
+    fe = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=True, fetch=args.fetch, **kw)
 
     def e2e_steps(n_steps, first):
         # submit(k), begin_fetch(k - depth + 2), end_fetch(k - depth + 1): depth - 1 batches stay in flight,
@@ -353,13 +355,13 @@ def run_ours(args):
             if k >= lag_b:
                 fe.begin_fetch(tick[k - lag_b])
             if k >= lag_e:
-                n = fe.end_fetch(tick[k - lag_e])[0]
-                fits += n
-                d2h += pipe.d2h_bytes(n)
+                r = fe.end_fetch(tick[k - lag_e])
+                fits += r[0]
+                d2h += pipe.d2h_bytes_psfs(r[1]) if args.fetch == "psfs" else pipe.d2h_bytes(r[0])
         for t in tick[max(0, n_steps - lag_e):]:
-            n = fe.end_fetch(t)[0]
-            fits += n
-            d2h += pipe.d2h_bytes(n)
+            r = fe.end_fetch(t)
+            fits += r[0]
+            d2h += pipe.d2h_bytes_psfs(r[1]) if args.fetch == "psfs" else pipe.d2h_bytes(r[0])
         return fits, d2h
 
     e2e_steps(max(3, args.depth), 0)
@@ -476,7 +478,10 @@ def run_ours(args):
         "host_enqueue_ms_per_step": host_enqueue_ms,
         "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": d2h // max(args.steps, 1), "frames_per_s": world * args.steps * N_FRAMES / (e2e_ms * 1e-3),
-                "api": "engine.FieldStream submit/begin_fetch/end_fetch over fsq_detect / fsq_fit_candidates (pinned host frames in, packed results out)"},
+                "returns": ("final PSF records of find_peptides (R^2 gate, consolidation, re-key on the device)" if args.fetch == "psfs"
+                            else "every candidate's fit record"),
+                "api": "engine.FieldStream submit/begin_fetch/end_fetch over fsq_detect / fsq_fit_candidates"
+                       + (" / fsq_consolidate / fsq_pack_psfs" if args.fetch == "psfs" else "") + " (pinned host frames in, packed results out)"},
         "gpu_launches": args.steps * fs.kernels_per_run,
         "clocks": clocks, "roofline": roofline, "roofline_detect": roofline_detect,
     }
@@ -503,6 +508,9 @@ def main():
     ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
                     help="fsq_lm_opts.warps_per_sm: warps per SM of ONE batch's LM launch (scheduling only; 0 = fill the SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fetch", default="psfs", choices=["psfs", "candidates"],
+                    help="what a step returns to the host in the e2e region: the final PSF records of find_peptides "
+                         "(R^2 gate + consolidation + re-key on the device; default) or every candidate's fit record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -42,7 +42,8 @@ constexpr int WNP = 7;
 constexpr int WNT = 28;
 constexpr int WTHREADS = 128;
 #ifndef WMINB
-#define WMINB 2      // 2 CTAs/SM (221 registers, no spills) measured faster than 3 (168 registers): same bulk rate, shorter tail
+#define WMINB 3      // 3 CTAs/SM (168 registers, no spills since the forward-differenced pass freed the FP64 tables):
+                     // +4..10 % in the pipelined step over 2 CTAs/SM (212 registers); 4 CTAs/SM (128 registers) spills and is slower
 #endif
 #define WQ_MACHEP 2.220446049250313e-16
 #define WQ_DWARF 2.2250738585072014e-308
@@ -398,7 +399,6 @@ lmwarp_kernel(const WarpArgs a) {
     bool nonfinite = false;
     double x[WNP], y[WNP];
     double ss0 = -1.0, ss1 = -1.0;                      // chi^2 at x, chi^2 of the last trial point
-    double sst = 0.0;                                   // total sum of squares of the window (pflib path)
     Lim<PFLIB> lim;
     lim.lo1 = 0.0; lim.lo = nullptr; lim.hi = nullptr; lim.qll = PF_QLL; lim.qul = PF_QUL;
     float delta = 0.0f, par = 0.0f, xnorm = 0.0f, gnorm = 0.0f, pnorm = 0.0f, prered = 0.0f, dirder = 0.0f, rss0 = 0.0f;
@@ -406,6 +406,9 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
     for (int j = 0; j < WNP; ++j) { x[j] = 0.0; y[j] = 1.0; diag[j] = 1.0f; iS[j] = 1.0f; }
 
+    // (Claiming one slot ahead per lane and prefetching its start record was measured on B200: it hides the two
+    //  round trips of a refill but a lane inside a 200-iteration fit then sits on an unstarted candidate, and the
+    //  40-frame launch got 10 % SLOWER (1.65 -> 1.82 ms); the queue stays strictly on demand.)
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         __syncwarp();
@@ -431,7 +434,6 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
                         for (int k = 0; k < P; ++k) sd[k * TPB] = (double)(int)WREC(k);
                         cand_h = (int)(WREC(28) >> 16); cand_w = (int)(WREC(28) & 0xffffu);
-                        sst = __hiloint2double((int)WREC(31), (int)WREC(30));
                         const int4 pre = make_int4((int)WREC(25), (int)WREC(26), (int)WREC(27), 0);
 #undef WREC
                         const double dmax = (double)pre.y, dmean = (double)pre.z / 25.0;
@@ -747,9 +749,9 @@ lmwarp_kernel(const WarpArgs a) {
                     o[0] = (x[2] + (double)cand_h) - 2.5;                                // pflib.py:461
                     o[1] = (x[3] + (double)cand_w) - 2.5;
                     o[2] = x[0]; o[3] = x[1]; o[4] = x[4]; o[5] = x[5]; o[6] = x[6];
-                    o[7] = sqrt(ss0 / 25.0); o[8] = 1.0 - ss0 / sst;   // ss0 = residual sum of squares at the final parameters
-                    o[10] = fmax(ss0, ss1);                                              // mpfit .fnorm (:1357-1359)
-                    o[11] = sqrt(ss0);
+                    o[7] = ss0;                 // residual sum of squares at the final parameters: fit_finish_kernel turns
+                    o[10] = fmax(ss0, ss1);     // it into rmse / r_2 / sqrt (FP64 sqrt and divisions at full lanes there);
+                                                // o[10] = mpfit .fnorm (:1357-1359)
                     *reinterpret_cast<int4*>(a.out_int + idx * 4) = make_int4(status, niter, nfev, n_damped);
                 } else {
 #pragma unroll
@@ -762,6 +764,20 @@ lmwarp_kernel(const WarpArgs a) {
             }
         }
     }
+}
+
+// r_2, rmse (pflib.py:463-472) and sqrt(chi^2) from the residual sum of squares the LM kernel left in column 7
+__global__ void __launch_bounds__(256)
+fit_finish_kernel(const WarpArgs a) {
+    long long n_total = a.n;
+    if (a.n_dev) { const long long nd = *a.n_dev; n_total = nd < a.n ? nd : a.n; }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    double* o = a.out_fit + i * 12;
+    const double ss0 = o[7];
+    o[7] = sqrt(ss0 / 25.0);
+    o[8] = 1.0 - ss0 / a.prep[i].sst;
+    o[11] = sqrt(ss0);
 }
 
 // model image at the fitted parameters (gaussfitter.py:252-254), one thread per fit
@@ -871,6 +887,8 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     FSQ_LAUNCH_CHECK();
     const int rc = launch_frame_path(a, head, st);
     if (rc != FSQ_OK) return rc;
+    fit_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    FSQ_LAUNCH_CHECK();
     if (fit_img) {
         fit_image_kernel<<<flat, 128, 0, st>>>(a);
         FSQ_LAUNCH_CHECK();

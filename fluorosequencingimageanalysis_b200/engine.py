@@ -315,6 +315,84 @@ def gaussfit_default_batch(windows, solver="fast", faithful=True, **kw):
     return r, p0
 
 
+PSF_GATED, PSF_DELETED, PSF_FINAL, PSF_REKEYED = 0, 1, 2, 3          # psf_state codes of fsq_consolidate (fsq.h)
+
+
+class Consolidation(object):
+    """Device result of consolidate_batch: per-candidate state / final key, final PSFs per frame."""
+    __slots__ = ("state", "key", "n_psf", "flags", "scratch")
+
+    def check(self):
+        """Raises the reference's AssertionError (pflib.py:518) if a re-keyed PSF landed on an occupied key."""
+        if int(self.flags.item()) & 1:
+            raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+
+
+def consolidate_batch(cand_hw, cand_frame, fit, n, n_frames, r_2_threshold=0.7, consolidation_radius=4,
+                      n_dev=None, out=None):
+    """R^2 gate + rival consolidation + re-key (pflib.py:466-468, 479-519) for the packed candidates of a batch
+    of frames, on the device (fsq_consolidate).  cand_hw [>=n,2] i32, cand_frame [>=n] i32, fit [>=n,12] f64
+    device tensors in the order fsq_detect emits; ``n_dev`` = device-resident candidate count (no host sync)."""
+    L = _lib.load()
+    require_cuda()
+    if consolidation_radius < 2:
+        raise ValueError("consolidation_radius must be at least 2")          # pflib.py:431-432
+    dev = fit.device
+    n = int(n)
+    r = out or Consolidation()
+    if out is None:
+        r.state = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        r.key = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
+        r.n_psf = torch.empty(max(int(n_frames), 1), dtype=torch.int64, device=dev)
+        r.flags = torch.empty(1, dtype=torch.int32, device=dev)
+        r.scratch = torch.empty(max(int(L.fsq_consolidate_scratch_bytes(n)), 1), dtype=torch.uint8, device=dev)
+    _lib.check(L.fsq_consolidate(_ptr(cand_hw), _ptr(cand_frame), _ptr(fit), n, _ptr(n_dev), int(n_frames),
+                                 float(r_2_threshold), int(consolidation_radius), _ptr(r.state), _ptr(r.key),
+                                 _ptr(r.n_psf), _ptr(r.flags), _ptr(r.scratch), r.scratch.numel(), _stream()))
+    return r
+
+
+class PackedPsfs(object):
+    """Final PSFs of a batch in the reference's dictionary order (fsq_pack_psfs): ``fit`` [m,12] (the
+    find_peptides 12-tuple minus the two 5x5 images, plus chi2 / fnorm), ``ints`` [m,4] = (frame, key_h, key_w,
+    candidate index), ``base`` [F+1] offsets of each frame's PSFs."""
+    __slots__ = ("fit", "ints", "base", "scratch")
+
+    def frame(self, f):
+        a, b = int(self.base[f]), int(self.base[f + 1])
+        return self.ints[a:b], self.fit[a:b]
+
+
+def pack_psfs_batch(cons, cand_frame, fit, n, n_frames, n_dev=None, cap_psf=None):
+    """fsq_pack_psfs: the survivors of ``consolidate_batch`` compacted on the device -> PackedPsfs (device tensors)."""
+    L = _lib.load()
+    dev = fit.device
+    n, F = int(n), int(n_frames)
+    cap = int(cap_psf if cap_psf is not None else max(n, 1))
+    r = PackedPsfs()
+    r.fit = torch.empty((cap, 12), dtype=torch.float64, device=dev)
+    r.ints = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    r.base = torch.empty(F + 1, dtype=torch.int64, device=dev)
+    r.scratch = torch.empty(max(int(L.fsq_pack_psfs_scratch_bytes(n, F)), 1), dtype=torch.uint8, device=dev)
+    _lib.check(L.fsq_pack_psfs(_ptr(cons.state), _ptr(cons.key), _ptr(cand_frame), _ptr(fit), n, _ptr(n_dev), F,
+                               _ptr(r.fit), _ptr(r.ints), _ptr(r.base), cap, _ptr(r.scratch), r.scratch.numel(), _stream()))
+    return r
+
+
+def psf_dict_order(state, cand_frame=None):
+    """Indices of the final PSFs in the reference's dictionary order (numpy, host): survivors that kept their
+    candidate pixel as key in raster order, then the re-keyed ones (`del` + `setdefault` moves an entry to the
+    end of the dict, pflib.py:514-519).  With ``cand_frame`` the order is per frame, frames in sequence."""
+    state = np.asarray(state)
+    keep = np.nonzero(state >= PSF_FINAL)[0]
+    moved = state[keep] == PSF_REKEYED
+    if cand_frame is None:
+        return np.concatenate([keep[~moved], keep[moved]])
+    fr = np.asarray(cand_frame)[keep]
+    order = np.lexsort((keep, moved, fr))                     # frame, then unmoved before moved, then raster
+    return keep[order]
+
+
 def metrics_batch(sub, fit):
     """pflib.py:463-473 for n (sub_img, fit_img) pairs -> [n,3] (r_2, rmse, s_n)."""
     L = _lib.load()
@@ -388,11 +466,14 @@ class FieldPipeline(object):
 
     def __init__(self, n_frames, H, W, dtype=None, cap_per_frame=None, faithful=True,
                  median_filter_size=5, correlation_matrix=DEFAULT_CORRELATION_MATRIX, c_std=2,
-                 device=None, solver="fast", park_after=None, warps_per_sm=None):
+                 device=None, solver="fast", park_after=None, warps_per_sm=None,
+                 consolidate=False, r_2_threshold=0.7, consolidation_radius=4, cap_psf_per_frame=None):
         require_cuda()
         self.L = _lib.load()
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.F, self.H, self.W = int(n_frames), int(H), int(W)
+        if consolidation_radius < 2:
+            raise ValueError("consolidation_radius must be at least 2")      # pflib.py:431-432
         if self.F > MAX_FRAMES_PER_CALL:
             raise ValueError("at most %d frames per pipeline batch" % MAX_FRAMES_PER_CALL)
         self.dtype = dtype if dtype is not None else torch.uint16
@@ -416,8 +497,27 @@ class FieldPipeline(object):
         self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
         self.fit_sbytes = self.L.fsq_fit_scratch_bytes(self.cap)
         self.fit_scratch = torch.empty(self.fit_sbytes, dtype=torch.uint8, device=d)
-        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (FAST: prep, phase 1, phase 2 when parking)
-        self.kernels_per_run = 6 + ((2 + (1 if self.opts.park_after > 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
+        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (FAST: prep, phase 1, phase 2 when parking, finish)
+        self.kernels_per_run = 6 + ((3 + (1 if self.opts.park_after > 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
+        # optional tail of find_peptides on the device: R^2 gate + consolidation + re-key (7 launches), packed
+        # final PSFs in dictionary order (3 launches) -- what then leaves the device is ~1 record per spot
+        self.consolidate = bool(consolidate)
+        if self.consolidate:
+            self.r2_thr, self.radius = float(r_2_threshold), int(consolidation_radius)
+            if cap_psf_per_frame is None:
+                cap_psf_per_frame = max(256, int(0.015 * H * W))
+            self.cap_psf = int(cap_psf_per_frame) * self.F
+            self.psf_state = torch.empty(self.cap, dtype=torch.uint8, device=d)
+            self.psf_key = torch.empty((self.cap, 2), dtype=torch.int32, device=d)
+            self.n_psf = torch.empty(self.F, dtype=torch.int64, device=d)
+            self.cons_flags = torch.empty(1, dtype=torch.int32, device=d)
+            self.cons_sbytes = max(self.L.fsq_consolidate_scratch_bytes(self.cap),
+                                   self.L.fsq_pack_psfs_scratch_bytes(self.cap, self.F))
+            self.cons_scratch = torch.empty(self.cons_sbytes, dtype=torch.uint8, device=d)
+            self.psf_fit = torch.empty((self.cap_psf, 12), dtype=torch.float64, device=d)
+            self.psf_int = torch.empty((self.cap_psf, 4), dtype=torch.int32, device=d)
+            self.psf_base = torch.zeros(self.F + 1, dtype=torch.int64, device=d)
+            self.kernels_per_run += 10
 
     def run(self, frames_dev, fit=True):
         """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype)."""
@@ -434,6 +534,30 @@ class FieldPipeline(object):
                                             _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
                                             ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
                                             None, _ptr(self.fit_scratch), self.fit_sbytes, st))
+            if self.consolidate:
+                _lib.check(L.fsq_consolidate(_ptr(self.cand_hw), _ptr(self.cand_frame), _ptr(self.out_fit), self.cap, n_dev,
+                                             self.F, self.r2_thr, self.radius, _ptr(self.psf_state), _ptr(self.psf_key),
+                                             _ptr(self.n_psf), _ptr(self.cons_flags), _ptr(self.cons_scratch),
+                                             self.cons_sbytes, st))
+                _lib.check(L.fsq_pack_psfs(_ptr(self.psf_state), _ptr(self.psf_key), _ptr(self.cand_frame), _ptr(self.out_fit),
+                                           self.cap, n_dev, self.F, _ptr(self.psf_fit), _ptr(self.psf_int), _ptr(self.psf_base),
+                                           self.cap_psf, _ptr(self.cons_scratch), self.cons_sbytes, st))
+
+    def total_psfs(self):
+        """Synchronising read of the number of final PSFs; raises if the PSF capacity was exceeded or the
+        reference's re-key assert (pflib.py:518) would have fired."""
+        m = int(self.psf_base[self.F].item())
+        if m > self.cap_psf:
+            raise _lib.FsqError("capacity: %d PSFs > cap %d; enlarge cap_psf_per_frame" % (m, self.cap_psf))
+        if int(self.cons_flags.item()) & 1:
+            raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+        return m
+
+    def fetch_psfs(self):
+        """-> (m, psf_int [m,4] (frame, key_h, key_w, candidate index), psf_fit [m,12], psf_base [F+1]) on the host"""
+        self.total()
+        m = self.total_psfs()
+        return m, self.psf_int[:m].cpu(), self.psf_fit[:m].cpu(), self.psf_base.cpu()
 
     def run_detect_only(self, frames_dev):
         self.run(frames_dev, fit=False)
@@ -475,6 +599,9 @@ class FieldPipeline(object):
     def d2h_bytes(self, n):
         return n * (12 * 8 + 4 * 4 + 2 * 4 + 4)
 
+    def d2h_bytes_psfs(self, m):
+        return m * (12 * 8 + 4 * 4) + (self.F + 1) * 8 + 16
+
 
 class FieldStream(object):
     """Software-pipelined production path: ``depth`` FieldPipeline slots, each on its own CUDA
@@ -490,19 +617,30 @@ class FieldStream(object):
     host then never waits for a batch it has just queued.  A slot is reused after ``depth`` submits; its
     previous results must have been fetched (or abandoned) by then."""
 
-    def __init__(self, n_frames, H, W, dtype=None, depth=3, host_io=True, **kw):
+    def __init__(self, n_frames, H, W, dtype=None, depth=3, host_io=True, fetch="candidates", **kw):
         require_cuda()
         self.depth = int(depth)
         self.slots = []
         self.host_io = host_io
+        if fetch not in ("candidates", "psfs"):
+            raise ValueError("fetch must be 'candidates' or 'psfs'")
+        self.fetch = fetch          # "psfs": consolidation on the device, only the final PSF records go to the host
+        if fetch == "psfs":
+            kw["consolidate"] = True
         for _ in range(self.depth):
             p = FieldPipeline(n_frames, H, W, dtype=dtype, **kw)
             sl = {"pipe": p, "stream": torch.cuda.Stream(device=p.dev),
                   "ev_count": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "n": None}
             if host_io:
                 sl["frames_dev"] = torch.empty((p.F, p.H, p.W), dtype=p.dtype, device=p.dev)
-                sl["pinned"] = p.pinned_buffers()
-                sl["count_host"] = torch.zeros(1, dtype=torch.int64).pin_memory()
+                sl["count_host"] = torch.zeros(4, dtype=torch.int64).pin_memory()
+                if fetch == "psfs":
+                    sl["pinned"] = {"psf_fit": torch.empty((p.cap_psf, 12), dtype=torch.float64).pin_memory(),
+                                    "psf_int": torch.empty((p.cap_psf, 4), dtype=torch.int32).pin_memory(),
+                                    "psf_base": torch.empty(p.F + 1, dtype=torch.int64).pin_memory(),
+                                    "flags": torch.zeros(1, dtype=torch.int32).pin_memory()}
+                else:
+                    sl["pinned"] = p.pinned_buffers()
             self.slots.append(sl)
         self.k = 0
         self.kernels_per_run = self.slots[0]["pipe"].kernels_per_run
@@ -518,7 +656,10 @@ class FieldStream(object):
                 frames = sl["frames_dev"]
             p.run(frames)
             if self.host_io:
-                sl["count_host"].copy_(p.n_cand[p.F:p.F + 1], non_blocking=True)
+                sl["count_host"][0:1].copy_(p.n_cand[p.F:p.F + 1], non_blocking=True)
+                if self.fetch == "psfs":
+                    sl["count_host"][1:2].copy_(p.psf_base[p.F:p.F + 1], non_blocking=True)
+                    sl["pinned"]["flags"].copy_(p.cons_flags, non_blocking=True)
                 sl["ev_count"].record(sl["stream"])
         sl["n"] = None
         return sl
@@ -530,6 +671,19 @@ class FieldStream(object):
         if n > p.cap:
             raise _lib.FsqError("capacity: %d candidates > cap %d; enlarge cap_per_frame" % (n, p.cap))
         pin = sl["pinned"]
+        if self.fetch == "psfs":
+            m = int(sl["count_host"][1])
+            if m > p.cap_psf:
+                raise _lib.FsqError("capacity: %d PSFs > cap %d; enlarge cap_psf_per_frame" % (m, p.cap_psf))
+            if int(pin["flags"][0]) & 1:
+                raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+            with torch.cuda.stream(sl["stream"]):
+                pin["psf_fit"][:m].copy_(p.psf_fit[:m], non_blocking=True)
+                pin["psf_int"][:m].copy_(p.psf_int[:m], non_blocking=True)
+                pin["psf_base"].copy_(p.psf_base, non_blocking=True)
+                sl["ev_done"].record(sl["stream"])
+            sl["n"], sl["m"] = n, m
+            return n
         with torch.cuda.stream(sl["stream"]):
             pin["fit"][:n].copy_(p.out_fit[:n], non_blocking=True)
             pin["ints"][:n].copy_(p.out_int[:n], non_blocking=True)
@@ -544,6 +698,9 @@ class FieldStream(object):
             self.begin_fetch(sl)
         sl["ev_done"].synchronize()
         n, pin = sl["n"], sl["pinned"]
+        if self.fetch == "psfs":        # (candidates fitted, final PSFs, psf_int [m,4], psf_fit [m,12], psf_base [F+1])
+            m = sl["m"]
+            return n, m, pin["psf_int"][:m], pin["psf_fit"][:m], pin["psf_base"]
         return n, pin["hw"][:n], pin["frame"][:n], pin["fit"][:n], pin["ints"][:n]
 
     def synchronize(self):

@@ -97,52 +97,26 @@ def consolidate_packed(cand_hw, fit, shape, r_2_threshold=0.7, consolidation_rad
     """R^2 gate + rival consolidation + re-key of pflib.py:466-468, 479-519 on packed arrays of
     ONE frame.  cand_hw [n,2] raster order, fit [n,>=10] (h_0,w_0,...,r_2 at column 8).
     Returns (keys [m,2] int, idx [m] indices into the candidate arrays) in dict-insertion order.
-    Host logic (next row 8(f)-1 moves it to the device)."""
+    Runs on the device (fsq_consolidate); raises the reference's AssertionError (:518) on a key collision."""
     if consolidation_radius < 2:
         raise ValueError("consolidation_radius must be at least 2")          # pflib.py:431-432
-    H, W = shape
+    import torch
+    engine.require_cuda()
+    cand_hw = np.asarray(cand_hw)
+    fit = np.asarray(fit, dtype=np.float64)
     n = cand_hw.shape[0]
-    r2 = fit[:, engine.COL_R2]
-    keep = ~(r2 < r_2_threshold)                                              # :466 discards only when '<'
-    grid = -np.ones((H, W), dtype=np.int64)
-    order = np.nonzero(keep)[0]
-    grid[cand_hw[order, 0], cand_hw[order, 1]] = order
-    alive = keep.copy()
-    h0 = fit[:, engine.COL_H0]
-    w0 = fit[:, engine.COL_W0]
-    rad = consolidation_radius
-    rr = rad ** 2
-    for i in order:
-        if not alive[i]:
-            continue
-        h, w = int(cand_hw[i, 0]), int(cand_hw[i, 1])
-        sl = grid[max(0, h - rad - 2):min(h + rad + 3, H), max(0, w - rad - 2):min(w + rad + 3, W)]
-        js = sl[sl >= 0]                                                      # raster order of (h_d, w_d)
-        for j in js:
-            if j == i or not alive[j]:
-                continue
-            if (h0[i] - h0[j]) ** 2 + (w0[i] - w0[j]) ** 2 > rr:
-                continue
-            if r2[i] > r2[j]:                                                 # :508
-                alive[j] = False
-                grid[cand_hw[j, 0], cand_hw[j, 1]] = -1
-            else:
-                alive[i] = False
-                grid[h, w] = -1
-                break
-    idx = np.nonzero(alive)[0]
-    # re-key (:514-519): delete + setdefault moves an entry to the END of the dict
-    bins = {}
-    for i in idx:
-        bins[(int(cand_hw[i, 0]), int(cand_hw[i, 1]))] = int(i)
-    for (h, w), i in list(bins.items()):
-        k = (int(_py2_round(h0[i])), int(_py2_round(w0[i])))
-        if k[0] != h or k[1] != w:
-            del bins[(h, w)]
-            assert k not in bins                                              # :518
-            bins.setdefault(k, i)
-    keys = np.array(list(bins.keys()), dtype=np.int64).reshape(-1, 2)
-    return keys, np.array(list(bins.values()), dtype=np.int64)
+    if n == 0:
+        return np.zeros((0, 2), dtype=np.int64), np.zeros(0, dtype=np.int64)
+    f12 = np.zeros((n, 12))
+    f12[:, :min(fit.shape[1], 12)] = fit[:, :12]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    c = engine.consolidate_batch(torch.from_numpy(np.ascontiguousarray(cand_hw.astype(np.int32))).to(dev),
+                                 torch.zeros(n, dtype=torch.int32, device=dev),
+                                 torch.from_numpy(np.ascontiguousarray(f12)).to(dev), n, 1,
+                                 r_2_threshold, consolidation_radius)
+    c.check()
+    idx = engine.psf_dict_order(c.state.cpu().numpy()[:n])
+    return c.key.cpu().numpy()[idx].astype(np.int64).reshape(-1, 2), idx.astype(np.int64)
 
 
 def find_peptides(image, median_filter_size=5, correlation_matrix=default_correlation_matrix,

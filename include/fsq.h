@@ -196,6 +196,48 @@ int64_t fsq_fit_scratch_bytes(int64_t n);
 int fsq_moments(const void* windows, int dtype_code, int64_t n, int win, const double* lo, const double* hi,
                 const uint8_t* lim_lo, const uint8_t* lim_hi, double* p0_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * R^2 gate + rival consolidation + re-key -- replaces the tail of pflib.find_peptides
+ * (pflib.py:466-468 `if r_2 < r_2_threshold: continue`, :479-512 the consolidation loop, :514-519 the
+ * re-key) for a whole batch of frames, on the packed records fsq_detect / fsq_fit_candidates wrote.
+ *   in   cand_hw [n,2], cand_frame [n]   candidates sorted by (frame, h, w) -- the order fsq_detect emits
+ *        out_fit [n,12]                  columns 0,1 = fitted centre h_0, w_0; column 8 = r_2
+ *        n, n_dev                        capacity / device-resident count (as fsq_fit_candidates)
+ *   out  psf_state [n] u8   0 = dropped by the R^2 gate, 1 = deleted by a rival, 2 = final PSF keyed by its
+ *                           candidate pixel, 3 = final PSF re-keyed to (round(h_0), round(w_0)) -- in the
+ *                           reference's dictionary such an entry moves to the END (delete + setdefault)
+ *        psf_key [n,2] i32  the final key (python-2 round(): half away from zero) of states 2/3
+ *        n_psf [n_frames] i64 (may be NULL)  final PSFs per frame
+ *        flags [1] i32      bit 0: a re-keyed PSF landed on an occupied key -- the reference's assert at
+ *                           pflib.py:518 would fire (impossible for pflib fits, whose centres stay within
+ *                           0.5 px of the candidate pixel; detected within the rival reach)
+ * The reference's result depends on its visiting order (raster) and on `>` at :508 (ties delete the visiting
+ * PSF); both are reproduced exactly: rivals form tiny connected components, each replayed sequentially.
+ * Returns FSQ_E_ARG for consolidation_radius < 2 (ValueError at pflib.py:431-432).
+ * ------------------------------------------------------------------------------------------ */
+int64_t fsq_consolidate_scratch_bytes(int64_t n);
+int fsq_consolidate(const int32_t* cand_hw, const int32_t* cand_frame, const double* out_fit, int64_t n,
+                    const int64_t* n_dev, int n_frames, double r_2_threshold, int consolidation_radius,
+                    uint8_t* psf_state, int32_t* psf_key, int64_t* n_psf, int32_t* flags,
+                    void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The final PSFs of a batch, packed in the order of the dictionary pflib.find_peptides returns
+ * (pflib.py:514-520): frames in sequence; inside a frame first the PSFs keyed by their candidate pixel
+ * in raster order, then the re-keyed ones (the reference deletes and re-inserts those, which appends).
+ *   in   psf_state, psf_key from fsq_consolidate; cand_frame, out_fit, n, n_dev as there
+ *   out  psf_fit [cap_psf,12] f64   the out_fit rows of the final PSFs
+ *        psf_int [cap_psf,4] i32    (frame, key_h, key_w, candidate index)
+ *        psf_base [n_frames+1] i64  offset of each frame's PSFs; psf_base[n_frames] = total (rows beyond
+ *                                   cap_psf are not written: compare the total with cap_psf)
+ * This is what leaves the device in the production pipeline: ~1 record per spot instead of ~10 candidates.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fsq_pack_psfs_scratch_bytes(int64_t n, int n_frames);
+int fsq_pack_psfs(const uint8_t* psf_state, const int32_t* psf_key, const int32_t* cand_frame,
+                  const double* out_fit, int64_t n, const int64_t* n_dev, int n_frames,
+                  double* psf_fit, int32_t* psf_int, int64_t* psf_base, int64_t cap_psf,
+                  void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);

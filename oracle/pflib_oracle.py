@@ -313,3 +313,56 @@ def photometry_maximum(image, h, w, radius=5, top=1):
     """flexlibrary.py:264-284 (background_adjust='none')."""
     r = np.sort(np.ravel(image_slice(image, h, w, radius)))
     return float(np.sum(r[-top:]))
+
+
+def consolidate_packed(cand_hw, fit, shape, r_2_threshold=0.7, consolidation_radius=4):
+    """R^2 gate + rival consolidation + re-key of pflib.py:466-468, 479-519 on packed arrays of
+    ONE frame.  cand_hw [n,2] raster order, fit [n,>=10] (h_0,w_0,...,r_2 at column 8).
+    Returns (keys [m,2] int, idx [m] indices into the candidate arrays) in dict-insertion order.
+    numpy restatement of the dictionary logic in `consolidate` above (pinned to it by tests/test_host_logic.py);
+    the checker of the device kernel fsq_consolidate."""
+    if consolidation_radius < 2:
+        raise ValueError("consolidation_radius must be at least 2")          # pflib.py:431-432
+    H, W = shape
+    n = cand_hw.shape[0]
+    r2 = fit[:, 8]
+    keep = ~(r2 < r_2_threshold)                                              # :466 discards only when '<'
+    grid = -np.ones((H, W), dtype=np.int64)
+    order = np.nonzero(keep)[0]
+    grid[cand_hw[order, 0], cand_hw[order, 1]] = order
+    alive = keep.copy()
+    h0 = fit[:, 0]
+    w0 = fit[:, 1]
+    rad = consolidation_radius
+    rr = rad ** 2
+    for i in order:
+        if not alive[i]:
+            continue
+        h, w = int(cand_hw[i, 0]), int(cand_hw[i, 1])
+        sl = grid[max(0, h - rad - 2):min(h + rad + 3, H), max(0, w - rad - 2):min(w + rad + 3, W)]
+        js = sl[sl >= 0]                                                      # raster order of (h_d, w_d)
+        for j in js:
+            if j == i or not alive[j]:
+                continue
+            if (h0[i] - h0[j]) ** 2 + (w0[i] - w0[j]) ** 2 > rr:
+                continue
+            if r2[i] > r2[j]:                                                 # :508
+                alive[j] = False
+                grid[cand_hw[j, 0], cand_hw[j, 1]] = -1
+            else:
+                alive[i] = False
+                grid[h, w] = -1
+                break
+    idx = np.nonzero(alive)[0]
+    # re-key (:514-519): delete + setdefault moves an entry to the END of the dict
+    bins = {}
+    for i in idx:
+        bins[(int(cand_hw[i, 0]), int(cand_hw[i, 1]))] = int(i)
+    for (h, w), i in list(bins.items()):
+        k = (int(py2_round(h0[i])), int(py2_round(w0[i])))
+        if k[0] != h or k[1] != w:
+            del bins[(h, w)]
+            assert k not in bins                                              # :518
+            bins.setdefault(k, i)
+    keys = np.array(list(bins.keys()), dtype=np.int64).reshape(-1, 2)
+    return keys, np.array(list(bins.values()), dtype=np.int64)

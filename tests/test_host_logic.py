@@ -92,20 +92,20 @@ def _packed_from_golden(g):
     return cands, fit
 
 
-def test_consolidate_packed_reproduces_reference_psf_keys(fits5):
+def test_oracle_consolidate_packed_reproduces_reference_psf_keys(fits5):
     """Fed with the REFERENCE's own per-candidate fits, the packed consolidation + re-key must
     return exactly the reference's final PSF dictionary keys (pflib.py:479-519); the
     insertion order is pinned by test_consolidate_packed_equals_oracle_dict_logic_random and
     the pipeline_small golden."""
     cands, fit = _packed_from_golden(fits5)
-    keys, idx = pflib.consolidate_packed(cands, fit, (512, 512))
+    keys, idx = po.consolidate_packed(cands, fit, (512, 512))     # (the device kernel: tests/test_gpu_consolidate.py)
     order = np.lexsort((keys[:, 1], keys[:, 0]))                  # the golden stores the keys sorted
     assert np.array_equal(keys[order], fits5["final_keys"])
     assert np.array_equal(fit[idx[order], 0], fits5["final_h0"])
     assert np.array_equal(fit[idx[order], 1], fits5["final_w0"])
 
 
-def test_consolidate_packed_equals_oracle_dict_logic_random():
+def test_oracle_consolidate_packed_equals_oracle_dict_logic_random():
     rng = np.random.default_rng(3)
     for trial in range(5):
         H = W = 60
@@ -126,9 +126,9 @@ def test_consolidate_packed_equals_oracle_dict_logic_random():
             want = po.consolidate(d, (H, W), radius)
         except AssertionError:
             with pytest.raises(AssertionError):
-                pflib.consolidate_packed(hw, fit, (H, W), 0.7, radius)
+                po.consolidate_packed(hw, fit, (H, W), 0.7, radius)
             continue
-        keys, idx = pflib.consolidate_packed(hw, fit, (H, W), 0.7, radius)
+        keys, idx = po.consolidate_packed(hw, fit, (H, W), 0.7, radius)
         assert [tuple(k) for k in keys.tolist()] == list(want.keys())
         assert idx.tolist() == [v[12] for v in want.values()]
 
