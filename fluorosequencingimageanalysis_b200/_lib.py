@@ -82,7 +82,7 @@ def load():
     L.fsq_moments.restype = i32
     L.fsq_moments.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp]
     L.fsq_consolidate_scratch_bytes.restype = i64
-    L.fsq_consolidate_scratch_bytes.argtypes = [i64]
+    L.fsq_consolidate_scratch_bytes.argtypes = [i64, i32]
     L.fsq_consolidate.restype = i32
     L.fsq_consolidate.argtypes = [vp, vp, vp, i64, vp, i32, dbl, i32, vp, vp, vp, vp, vp, i64, vp]
     L.fsq_pack_psfs_scratch_bytes.restype = i64

@@ -9,45 +9,58 @@
 //
 // What makes it parallel: two PSFs interact only if they are rivals (pixels within radius + 2 on both axes AND
 // centres within radius).  The sequential process therefore factorises exactly over the connected components
-// of the rival graph, which are tiny (the ~3-6 accepted candidates around one spot).  So:
+// of the rival graph, which are tiny (the ~5 accepted candidates around one spot).  So:
 //   cons_count / cons_scan / cons_scatter   order-preserving compaction of the accepted candidates (R^2 gate)
-//   cons_union     lock-free union-find over rival pairs (larger root hooked under the smaller one, so a
-//                  component's root is its FIRST member in raster order)
-//   cons_flatten   label = root
-//   cons_process   one thread per component replays the reference's loop over the component's members in
-//                  raster order (members are found by scanning forward while the row gap stays <= radius + 2)
-//   cons_finish    states, python-2 rounding of the fitted centre -> new key, the reference's collision assert
-//                  (:518) as a flag, survivors per frame
+//   cons_adj        every accepted candidate lists its rivals, in raster order (one scan of its window rows;
+//                   headers are fetched eight at a time, predicates are branch-free)
+//   cons_component  breadth-first walk over the rival lists; a candidate that meets an EARLIER member leaves at
+//                   once, so only the first member of each component finishes the walk -- and then replays the
+//                   reference's loop over the members in raster order (no atomics, no iteration to convergence)
+//   cons_fallback   frames whose rival graph exceeds the fixed limits of those two kernels (> 16 rivals, > 64 members:
+//                   synthetic / extremely dense inputs) are redone by one thread each, scanning window rows directly
+//   cons_finish     states, python-2 rounding of the fitted centre -> new key, the reference's collision assert
+//                   (:518) as a flag, survivors per frame
+// (A first version -- lock-free union-find + one thread per component scanning window rows -- ran with 2.3 of 32
+//  lanes active and took 0.36 ms per 40-frame batch; ncu: profiles/r01j_cons_unionfind_kernels.txt.)
 #include "fsq_common.cuh"
 
 namespace fsq {
 
-struct __align__(8) ConsRec {
-    int f, h, w, idx;          // frame, candidate pixel, index into the candidate arrays
-    double h0, w0, r2;         // fitted centre (image coordinates), R^2
-};
-static_assert(sizeof(ConsRec) == 40, "ConsRec must be 40 bytes");
+// One accepted candidate = a 16-byte header (what the window scans read: eight of them are fetched at a time, the
+// scans are latency chains otherwise) + the three doubles the rival test needs (read only for pixels in the window).
+struct __align__(16) ConsHdr { int f, h, w, idx; };     // frame, candidate pixel, index into the candidate arrays
+struct __align__(8) ConsVal { double h0, w0, r2; };      // fitted centre (image coordinates), R^2
+constexpr int CONS_BATCH = 8;
+constexpr int CONS_MAXDEG = 16;     // rivals per accepted candidate (config-1 data: mean 3.6, max 7)
+constexpr int CONS_MAXCOMP = 64;    // members per component (config-1 data: mean 4.2, max 12)
+                                    // a frame beyond either limit is redone by cons_fallback_kernel (one thread, exact)
 
 struct ConsScratch {
     long long* m_total;        // [1] number of accepted candidates (header)
     int* blockcount;           // [nb + 1] accepted per block of 256 candidates -> exclusive offsets
-    int* parent;               // [n] union-find forest over accepted positions, then the flattened labels
     unsigned char* alive;      // [n]
-    ConsRec* rec;              // [n]
+    unsigned char* deg;        // [n] number of rivals
+    short* adj;                // [n][CONS_MAXDEG] rival positions relative to the own position, raster order
+    int* frame_over;           // [F] frame holds a candidate / component beyond CONS_MAXDEG / CONS_MAXCOMP
+    ConsHdr* hdr;              // [n]
+    ConsVal* val;              // [n]
 };
 
 static inline long long cons_align(long long x) { return (x + 255) & ~255LL; }
 
-static long long cons_carve(ConsScratch* s, char* base, long long n) {
+static long long cons_carve(ConsScratch* s, char* base, long long n, int F) {
     long long off = 0;
     auto take = [&](long long bytes) { char* p = base ? base + off : nullptr; off += cons_align(bytes); return p; };
     const long long nb = (n + 255) / 256;
     char* p;
     p = take(64);                          if (s) s->m_total = (long long*)p;
     p = take((nb + 1) * 4);                if (s) s->blockcount = (int*)p;
-    p = take(n * 4);                       if (s) s->parent = (int*)p;
     p = take(n);                           if (s) s->alive = (unsigned char*)p;
-    p = take(n * (long long)sizeof(ConsRec)); if (s) s->rec = (ConsRec*)p;
+    p = take(n);                           if (s) s->deg = (unsigned char*)p;
+    p = take(n * 2 * CONS_MAXDEG);         if (s) s->adj = (short*)p;
+    p = take(((long long)F + 1) * 4);      if (s) s->frame_over = (int*)p;
+    p = take(n * (long long)sizeof(ConsHdr)); if (s) s->hdr = (ConsHdr*)p;
+    p = take(n * (long long)sizeof(ConsVal)); if (s) s->val = (ConsVal*)p;
     return off;
 }
 
@@ -116,79 +129,159 @@ cons_scatter_kernel(const double* __restrict__ fit, long long n, const long long
     for (int k = 0; k < warp; ++k) before += wsum[k];
     if (keep) {
         const int pos = blockoff[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
-        ConsRec r;
-        r.f = cand_frame[i]; r.h = cand_hw[2 * i]; r.w = cand_hw[2 * i + 1]; r.idx = (int)i;
-        r.h0 = fit[i * 12 + 0]; r.w0 = fit[i * 12 + 1]; r.r2 = fit[i * 12 + 8];
-        s.rec[pos] = r;
-        s.parent[pos] = pos;
+        ConsHdr hd;
+        hd.f = cand_frame[i]; hd.h = cand_hw[2 * i]; hd.w = cand_hw[2 * i + 1]; hd.idx = (int)i;
+        ConsVal v;
+        v.h0 = fit[i * 12 + 0]; v.w0 = fit[i * 12 + 1]; v.r2 = fit[i * 12 + 8];
+        *reinterpret_cast<int4*>(&s.hdr[pos]) = *reinterpret_cast<const int4*>(&hd);
+        s.val[pos] = v;
         s.alive[pos] = 1;
     }
 }
 
 // (h_0 - h_0')^2 + (w_0 - w_0')^2 > radius^2 in the reference's arithmetic (no contraction)
-__device__ __forceinline__ bool cons_far(const ConsRec& a, const ConsRec& b, double rr) {
+__device__ __forceinline__ bool cons_far(const ConsVal& a, const ConsVal& b, double rr) {
     const double dh = a.h0 - b.h0, dw = a.w0 - b.w0;
     return __dadd_rn(__dmul_rn(dh, dh), __dmul_rn(dw, dw)) > rr;
 }
 
-__device__ __forceinline__ int cons_find(const volatile int* parent, int x) {
-    int p;
-    while ((p = parent[x]) != x) x = p;
-    return x;
+__device__ __forceinline__ ConsHdr cons_ld_hdr(const ConsHdr* hdr, long long i) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(hdr + i));
+    ConsHdr r; r.f = q.x; r.h = q.y; r.w = q.z; r.idx = q.w;
+    return r;
 }
 
+// rival lists: accepted candidates of the same frame whose pixel lies within +-reach on both axes (the window of
+// pflib.py:492-495) and whose fitted centre lies within the radius (:505), in raster order
 __global__ void __launch_bounds__(128)
-cons_union_kernel(ConsScratch s, int reach, double rr) {
+cons_adj_kernel(ConsScratch s, int reach, double rr) {
     const long long m = *s.m_total;
     const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
     if (a >= m) return;
-    const ConsRec ra = s.rec[a];
-    for (long long b = a - 1; b >= 0; --b) {                   // earlier rivals; later ones find this PSF themselves
-        const ConsRec rb = s.rec[b];
-        if (rb.f != ra.f || rb.h < ra.h - reach) break;
-        if (abs(rb.w - ra.w) > reach || cons_far(ra, rb, rr)) continue;
-        int x = (int)a, y = (int)b;
-        for (;;) {
-            x = cons_find(s.parent, x); y = cons_find(s.parent, y);
-            if (x == y) break;
-            if (x < y) { const int t = x; x = y; y = t; }      // hook the larger root under the smaller
-            if (atomicCAS(&s.parent[x], x, y) == x) break;
+    const ConsHdr ha = cons_ld_hdr(s.hdr, a);
+    const ConsVal va = s.val[a];
+    // first accepted position inside the window rows (the list is sorted by frame, row, column)
+    long long lo = a;
+    for (long long base = a - 1; base >= 0; base -= CONS_BATCH) {
+        ConsHdr hb[CONS_BATCH];
+#pragma unroll
+        for (int q = 0; q < CONS_BATCH; ++q) hb[q] = cons_ld_hdr(s.hdr, base - q >= 0 ? base - q : 0);
+        bool last_in = false;
+#pragma unroll
+        for (int q = 0; q < CONS_BATCH; ++q) {
+            const long long b = base - q;
+            const bool in = (b >= 0) && (hb[q].f == ha.f) && (hb[q].h >= ha.h - reach);
+            lo = in ? b : lo;                                  // `in` is monotone along the scan
+            last_in = in;
+        }
+        if (!last_in) break;
+    }
+    int deg = 0;
+    bool over = false;
+    short* adj = s.adj + a * CONS_MAXDEG;
+    for (long long base = lo; base < m; base += CONS_BATCH) {
+        ConsHdr hj[CONS_BATCH];
+#pragma unroll
+        for (int q = 0; q < CONS_BATCH; ++q) hj[q] = cons_ld_hdr(s.hdr, base + q < m ? base + q : m - 1);
+        bool last_in = false;
+#pragma unroll
+        for (int q = 0; q < CONS_BATCH; ++q) {
+            const long long j = base + q;
+            const bool in = (j < m) && (hj[q].f == ha.f) && (hj[q].h <= ha.h + reach);
+            last_in = in;
+            if (in && j != a && abs(hj[q].w - ha.w) <= reach) {
+                const ConsVal vj = s.val[j];
+                if (!cons_far(va, vj, rr)) {
+                    const long long off = j - a;
+                    if (deg < CONS_MAXDEG && off >= -32768 && off <= 32767) adj[deg] = (short)off;
+                    else over = true;
+                    ++deg;
+                }
+            }
+        }
+        if (!last_in) break;
+    }
+    if (over) { atomicOr(&s.frame_over[ha.f], 1); deg = deg < CONS_MAXDEG ? deg : CONS_MAXDEG; }
+    s.deg[a] = (unsigned char)deg;
+}
+
+// one walk per accepted candidate; only the first member of a component completes it and replays pflib.py:479-512
+__global__ void __launch_bounds__(128)
+cons_component_kernel(ConsScratch s) {
+    const long long m = *s.m_total;
+    const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (a >= m) return;
+    int member[CONS_MAXCOMP];
+    int cnt = 1;
+    member[0] = (int)a;
+    for (int i = 0; i < cnt; ++i) {
+        const int k = member[i];
+        const int dk = s.deg[k];
+        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
+        for (int r = 0; r < dk; ++r) {
+            const int j = k + adj[r];
+            if (j < (int)a) return;                            // an earlier member exists: it does the work
+            bool seen = false;
+            for (int t = 0; t < cnt; ++t) seen |= (member[t] == j);
+            if (!seen) {
+                if (cnt < CONS_MAXCOMP) member[cnt++] = j;
+                else atomicOr(&s.frame_over[s.hdr[a].f], 1);
+            }
+        }
+    }
+    // raster order = ascending position (insertion sort; the walk leaves the list nearly sorted)
+    for (int i = 1; i < cnt; ++i) {
+        const int v = member[i];
+        int t = i - 1;
+        while (t >= 0 && member[t] > v) { member[t + 1] = member[t]; --t; }
+        member[t + 1] = v;
+    }
+    for (int i = 0; i < cnt; ++i) {
+        const int k = member[i];
+        if (!s.alive[k]) continue;                             // "skip pixels that have had their psfs deleted" (:481)
+        const double r2k = s.val[k].r2;
+        const int dk = s.deg[k];
+        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
+        for (int r = 0; r < dk; ++r) {                         // itertools.product(h_range, w_range): raster order
+            const int j = k + adj[r];
+            if (!s.alive[j]) continue;
+            if (r2k > s.val[j].r2) s.alive[j] = 0;             // :508-509
+            else { s.alive[k] = 0; break; }                    // :510-512
         }
     }
 }
 
-__global__ void __launch_bounds__(128)
-cons_flatten_kernel(ConsScratch s, int* __restrict__ label) {
+// Exact fallback for frames whose rival graph exceeds the limits of the two kernels above (extremely dense or
+// synthetic inputs): one thread replays pflib.py:479-512 over the whole frame, scanning window rows directly.
+__global__ void __launch_bounds__(32)
+cons_fallback_kernel(ConsScratch s, int F, int reach, double rr) {
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    if (f >= F || !s.frame_over[f]) return;
     const long long m = *s.m_total;
-    const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (a >= m) return;
-    label[a] = cons_find(s.parent, (int)a);
-}
-
-// one thread per component: the reference's loop (pflib.py:479-512) over the members in raster order
-__global__ void __launch_bounds__(128)
-cons_process_kernel(ConsScratch s, const int* __restrict__ label, int reach, double rr) {
-    const long long m = *s.m_total;
-    const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (a >= m || label[a] != (int)a) return;
-    const int f = s.rec[a].f;
-    int maxrow = s.rec[a].h;
-    for (long long k = a; k < m; ++k) {
-        const ConsRec rk = s.rec[k];
-        if (rk.f != f || rk.h > maxrow + reach) break;         // no member can lie further down (rows of rivals differ by <= reach)
-        if (label[k] != (int)a) continue;
-        maxrow = rk.h;
-        if (!s.alive[k]) continue;                             // "skip pixels that have had their psfs deleted" (:481)
-        long long j = k;
-        while (j > 0 && s.rec[j - 1].f == f && s.rec[j - 1].h >= rk.h - reach) --j;
-        for (; j < m; ++j) {                                   // itertools.product(h_range, w_range): raster order
-            const ConsRec rj = s.rec[j];
-            if (rj.f != f || rj.h > rk.h + reach) break;
-            if (j == k || abs(rj.w - rk.w) > reach) continue;
-            if (cons_far(rk, rj, rr)) continue;                // (other components' alive flags are never read)
-            if (!s.alive[j]) continue;
-            if (rk.r2 > rj.r2) s.alive[j] = 0;                 // :508-509
-            else { s.alive[k] = 0; break; }                    // :510-512
+    long long beg, end;                                        // [beg, end) = accepted candidates of frame f (sorted by frame)
+    {
+        long long a = 0, b = m;
+        while (a < b) { const long long c = (a + b) / 2; if (s.hdr[c].f < f) a = c + 1; else b = c; }
+        beg = a;
+        b = m;
+        while (a < b) { const long long c = (a + b) / 2; if (s.hdr[c].f <= f) a = c + 1; else b = c; }
+        end = a;
+    }
+    for (long long k = beg; k < end; ++k) s.alive[k] = 1;
+    long long lo = beg;
+    for (long long k = beg; k < end; ++k) {
+        if (!s.alive[k]) continue;
+        const ConsHdr hk = s.hdr[k];
+        const ConsVal vk = s.val[k];
+        while (s.hdr[lo].h < hk.h - reach) ++lo;
+        for (long long j = lo; j < end; ++j) {
+            const ConsHdr hj = s.hdr[j];
+            if (hj.h > hk.h + reach) break;
+            if (j == k || abs(hj.w - hk.w) > reach) continue;
+            const ConsVal vj = s.val[j];
+            if (cons_far(vk, vj, rr) || !s.alive[j]) continue;
+            if (vk.r2 > vj.r2) s.alive[j] = 0;
+            else { s.alive[k] = 0; break; }
         }
     }
 }
@@ -199,25 +292,33 @@ cons_finish_kernel(ConsScratch s, int reach, unsigned char* __restrict__ psf_sta
     const long long m = *s.m_total;
     const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
     if (a >= m) return;
-    const ConsRec ra = s.rec[a];
-    if (!s.alive[a]) { psf_state[ra.idx] = 1; return; }
-    const int kh = (int)round(ra.h0), kw = (int)round(ra.w0);  // python-2 round(): half away from zero (:515)
-    const bool moved = (kh != ra.h) || (kw != ra.w);
-    psf_state[ra.idx] = moved ? 3 : 2;
-    psf_key[2 * ra.idx] = kh; psf_key[2 * ra.idx + 1] = kw;
-    if (n_psf) atomicAdd(&n_psf[ra.f], 1ull);
+    const ConsHdr ha = cons_ld_hdr(s.hdr, a);
+    if (!s.alive[a]) { psf_state[ha.idx] = 1; return; }
+    const ConsVal va = s.val[a];
+    const int kh = (int)round(va.h0), kw = (int)round(va.w0);  // python-2 round(): half away from zero (:515)
+    const bool moved = (kh != ha.h) || (kw != ha.w);
+    psf_state[ha.idx] = moved ? 3 : 2;
+    psf_key[2 * ha.idx] = kh; psf_key[2 * ha.idx + 1] = kw;
+    if (n_psf) atomicAdd(&n_psf[ha.f], 1ull);
     if (moved) {
         // :518 asserts that the new key is free at the moment of the move: earlier survivors sit at their FINAL
         // keys by then, later ones still at their candidate pixels.  (Cannot happen when the fitted centre lies
         // within 0.5 px of the candidate pixel, as it does for pflib fits; checked within the rival reach.)
         long long b = a;
-        while (b > 0 && s.rec[b - 1].f == ra.f && s.rec[b - 1].h >= kh - reach - 1) --b;
-        for (; b < m; ++b) {
-            const ConsRec rb = s.rec[b];
-            if (rb.f != ra.f || rb.h > kh + reach + 1) break;
-            if (b == a || !s.alive[b]) continue;
-            const int bh = b < a ? (int)round(rb.h0) : rb.h, bw = b < a ? (int)round(rb.w0) : rb.w;
-            if (bh == kh && bw == kw) atomicOr(flags, 1);
+        while (b > 0 && s.hdr[b - 1].f == ha.f && s.hdr[b - 1].h >= kh - reach - 1) --b;
+        bool stop = false;
+        for (; b < m && !stop; b += CONS_BATCH) {
+            ConsHdr hb[CONS_BATCH];
+#pragma unroll
+            for (int q = 0; q < CONS_BATCH; ++q) hb[q] = cons_ld_hdr(s.hdr, b + q < m ? b + q : m - 1);
+#pragma unroll
+            for (int q = 0; q < CONS_BATCH; ++q) {
+                const long long c = b + q;
+                if (stop || c >= m || hb[q].f != ha.f || hb[q].h > kh + reach + 1) { stop = true; continue; }
+                if (c == a || abs(hb[q].w - kw) > reach + 1 || !s.alive[c]) continue;
+                const int bh = c < a ? (int)round(s.val[c].h0) : hb[q].h, bw = c < a ? (int)round(s.val[c].w0) : hb[q].w;
+                if (bh == kh && bw == kw) atomicOr(flags, 1);
+            }
         }
     }
 }
@@ -328,8 +429,8 @@ pack_scatter_kernel(const unsigned char* __restrict__ state, const int32_t* __re
 
 using namespace fsq;
 
-extern "C" int64_t fsq_consolidate_scratch_bytes(int64_t n) {
-    return cons_carve(nullptr, nullptr, n > 0 ? n : 0) + cons_align((n > 0 ? n : 0) * 4);
+extern "C" int64_t fsq_consolidate_scratch_bytes(int64_t n, int n_frames) {
+    return cons_carve(nullptr, nullptr, n > 0 ? n : 0, n_frames > 0 ? n_frames : 0);
 }
 
 extern "C" int fsq_consolidate(const int32_t* cand_hw, const int32_t* cand_frame, const double* out_fit, int64_t n,
@@ -346,13 +447,14 @@ extern "C" int fsq_consolidate(const int32_t* cand_hw, const int32_t* cand_frame
         set_error("fsq_consolidate: NULL pointer argument");
         return FSQ_E_ARG;
     }
-    if (scratch_bytes < fsq_consolidate_scratch_bytes(n)) {
-        set_error("fsq_consolidate: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)fsq_consolidate_scratch_bytes(n));
+    if (n_frames <= 0) { set_error("fsq_consolidate: n_frames must be positive"); return FSQ_E_ARG; }
+    if (scratch_bytes < fsq_consolidate_scratch_bytes(n, n_frames)) {
+        set_error("fsq_consolidate: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)fsq_consolidate_scratch_bytes(n, n_frames));
         return FSQ_E_CAPACITY;
     }
     ConsScratch s;
-    const long long used = cons_carve(&s, (char*)scratch, n);
-    int* label = (int*)((char*)scratch + used);
+    cons_carve(&s, (char*)scratch, n, n_frames);
+    FSQ_CUDA_CHECK(cudaMemsetAsync(s.frame_over, 0, sizeof(int) * (size_t)n_frames, st));
     const long long nb = (n + 255) / 256;
     const unsigned g128 = (unsigned)((n + 127) / 128);
     const int reach = consolidation_radius + 2;                                          // pflib.py:492-495
@@ -364,11 +466,11 @@ extern "C" int fsq_consolidate(const int32_t* cand_hw, const int32_t* cand_frame
     FSQ_LAUNCH_CHECK();
     cons_scatter_kernel<<<(unsigned)nb, 256, 0, st>>>(out_fit, n, nd, r_2_threshold, cand_hw, cand_frame, s.blockcount, s);
     FSQ_LAUNCH_CHECK();
-    cons_union_kernel<<<g128, 128, 0, st>>>(s, reach, rr);
+    cons_adj_kernel<<<g128, 128, 0, st>>>(s, reach, rr);
     FSQ_LAUNCH_CHECK();
-    cons_flatten_kernel<<<g128, 128, 0, st>>>(s, label);
+    cons_component_kernel<<<g128, 128, 0, st>>>(s);
     FSQ_LAUNCH_CHECK();
-    cons_process_kernel<<<g128, 128, 0, st>>>(s, label, reach, rr);
+    cons_fallback_kernel<<<(unsigned)((n_frames + 31) / 32), 32, 0, st>>>(s, n_frames, reach, rr);
     FSQ_LAUNCH_CHECK();
     cons_finish_kernel<<<g128, 128, 0, st>>>(s, reach, psf_state, psf_key, (unsigned long long*)n_psf, flags);
     FSQ_LAUNCH_CHECK();

@@ -324,8 +324,12 @@ class Consolidation(object):
 
     def check(self):
         """Raises the reference's AssertionError (pflib.py:518) if a re-keyed PSF landed on an occupied key."""
-        if int(self.flags.item()) & 1:
-            raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+        check_consolidation_flags(int(self.flags.item()))
+
+
+def check_consolidation_flags(v):
+    if v & 1:
+        raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
 
 
 def consolidate_batch(cand_hw, cand_frame, fit, n, n_frames, r_2_threshold=0.7, consolidation_radius=4,
@@ -345,7 +349,7 @@ def consolidate_batch(cand_hw, cand_frame, fit, n, n_frames, r_2_threshold=0.7, 
         r.key = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
         r.n_psf = torch.empty(max(int(n_frames), 1), dtype=torch.int64, device=dev)
         r.flags = torch.empty(1, dtype=torch.int32, device=dev)
-        r.scratch = torch.empty(max(int(L.fsq_consolidate_scratch_bytes(n)), 1), dtype=torch.uint8, device=dev)
+        r.scratch = torch.empty(max(int(L.fsq_consolidate_scratch_bytes(n, int(n_frames))), 1), dtype=torch.uint8, device=dev)
     _lib.check(L.fsq_consolidate(_ptr(cand_hw), _ptr(cand_frame), _ptr(fit), n, _ptr(n_dev), int(n_frames),
                                  float(r_2_threshold), int(consolidation_radius), _ptr(r.state), _ptr(r.key),
                                  _ptr(r.n_psf), _ptr(r.flags), _ptr(r.scratch), r.scratch.numel(), _stream()))
@@ -511,7 +515,7 @@ class FieldPipeline(object):
             self.psf_key = torch.empty((self.cap, 2), dtype=torch.int32, device=d)
             self.n_psf = torch.empty(self.F, dtype=torch.int64, device=d)
             self.cons_flags = torch.empty(1, dtype=torch.int32, device=d)
-            self.cons_sbytes = max(self.L.fsq_consolidate_scratch_bytes(self.cap),
+            self.cons_sbytes = max(self.L.fsq_consolidate_scratch_bytes(self.cap, self.F),
                                    self.L.fsq_pack_psfs_scratch_bytes(self.cap, self.F))
             self.cons_scratch = torch.empty(self.cons_sbytes, dtype=torch.uint8, device=d)
             self.psf_fit = torch.empty((self.cap_psf, 12), dtype=torch.float64, device=d)
@@ -549,8 +553,7 @@ class FieldPipeline(object):
         m = int(self.psf_base[self.F].item())
         if m > self.cap_psf:
             raise _lib.FsqError("capacity: %d PSFs > cap %d; enlarge cap_psf_per_frame" % (m, self.cap_psf))
-        if int(self.cons_flags.item()) & 1:
-            raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+        check_consolidation_flags(int(self.cons_flags.item()))
         return m
 
     def fetch_psfs(self):
@@ -675,8 +678,7 @@ class FieldStream(object):
             m = int(sl["count_host"][1])
             if m > p.cap_psf:
                 raise _lib.FsqError("capacity: %d PSFs > cap %d; enlarge cap_psf_per_frame" % (m, p.cap_psf))
-            if int(pin["flags"][0]) & 1:
-                raise AssertionError("re-keyed PSF collides with an existing key (pflib.py:518)")
+            check_consolidation_flags(int(pin["flags"][0]))
             with torch.cuda.stream(sl["stream"]):
                 pin["psf_fit"][:m].copy_(p.psf_fit[:m], non_blocking=True)
                 pin["psf_int"][:m].copy_(p.psf_int[:m], non_blocking=True)

@@ -215,7 +215,7 @@ int fsq_moments(const void* windows, int dtype_code, int64_t n, int win, const d
  * PSF); both are reproduced exactly: rivals form tiny connected components, each replayed sequentially.
  * Returns FSQ_E_ARG for consolidation_radius < 2 (ValueError at pflib.py:431-432).
  * ------------------------------------------------------------------------------------------ */
-int64_t fsq_consolidate_scratch_bytes(int64_t n);
+int64_t fsq_consolidate_scratch_bytes(int64_t n, int n_frames);
 int fsq_consolidate(const int32_t* cand_hw, const int32_t* cand_frame, const double* out_fit, int64_t n,
                     const int64_t* n_dev, int n_frames, double r_2_threshold, int consolidation_radius,
                     uint8_t* psf_state, int32_t* psf_key, int64_t* n_psf, int32_t* flags,
