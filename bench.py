@@ -433,11 +433,12 @@ def run_ours(args):
     det_traffic = traffic.get("detect_cm_packed_kernel", {}).get("bytes")
     det_bytes = N_FRAMES * H * W * 2 + 8 * n_last
     det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
-    kname = {"fast": "lmwarp_kernel phase 1 + phase 2 (+ fit_prep_kernel) behind fsq_fit_candidates",
+    kname = {"fast": "lmwarp_kernel (+ fit_prep_kernel, fit_finish_kernel) behind fsq_fit_candidates",
              "fast64": "lmfast_kernel<double,true>", "minpack": "lmfit_kernel<8,true>"}[solver]
     roofline = {"bound": pk, "achieved": achieved, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (peak[pk] / 1e12), "traffic": lm_traffic,
                 "achieved_in_pipeline": flops / n_last * (fits_all / world / args.steps) / (ms_total / args.steps * 1e-3) / 1e12,
+                "frac_in_pipeline": flops / n_last * (fits_all / world / args.steps) / (ms_total / args.steps * 1e-3) / peak[pk],
                 "kernel": kname, "ms_per_launch": fit_ms_avg,
                 "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "passes_per_launch": sum_nfev,
                 "flop_per_lm_iteration": fl_iter,
