@@ -432,6 +432,18 @@ def photometry_batch(frames, spots_hw, spot_frame, method="mexican_hat", radius=
     return out
 
 
+def photometry_from_fit(fit, method="gaussian_volume", scaling=10 ** 6):
+    """The two Spot.photometry methods that only read the Gaussian fit (flexlibrary.py:212-241), for packed PSF
+    records [n,12] (torch or numpy; same multiplication order as the reference):
+    'gaussian_volume' = scaling * A * sigma_h * sigma_w, 'sigmas' = scaling * sigma_h * sigma_w."""
+    A, sh, sw = fit[:, COL_A], fit[:, COL_SIGMA_H], fit[:, COL_SIGMA_W]
+    if method == "gaussian_volume":
+        return float(scaling) * A * sh * sw
+    if method == "sigmas":
+        return float(scaling) * sh * sw
+    raise ValueError("Uknown method specified.")                             # flexlibrary.py:315
+
+
 class FieldResults(object):
     """Packed per-candidate results of find_peptides_batch (host numpy after .cpu())."""
     __slots__ = ("cand_hw", "cand_frame", "n_cand", "thr", "fit", "ints", "fit_img", "shape")
