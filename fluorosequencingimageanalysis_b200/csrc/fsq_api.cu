@@ -149,27 +149,6 @@ photometry_kernel(const void* __restrict__ frames, int dtype, int H, int W,
 //  elements, plain sequential otherwise and across rows for axis=0), with explicit _rn intrinsics so
 //  that no product is contracted into an FMA: float64 windows give the reference's bits.
 constexpr int MO_MAXW = 11;
-template <class F>
-__device__ __forceinline__ double np_sum(int n, F f) {         // numpy pairwise_sum for n < 128
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; ++i) r = __dadd_rn(r, f(i));
-        return r;
-    }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = f(j);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i + j));
-    }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, f(i));
-    return res;
-}
-
 __global__ void __launch_bounds__(128)
 moments_kernel(const void* __restrict__ windows, int dtype, long long n, int win, double* out,
                const double* __restrict__ lo, const double* __restrict__ hi,
@@ -260,6 +239,105 @@ moments_kernel(const void* __restrict__ windows, int dtype, long long n, int win
             if (lim_lo[lane] && v < lo[lane]) v = lo[lane];
             out[i * 7 + lane] = v;
         }
+    }
+}
+
+// ---- luminosity-centroid particle tracking (flexlibrary.py:1173-1317), one warp per spot ----------------------
+//  For every spot of frame 0 and every later frame f: take the (2R+1)^2 window of frame f around the spot's last
+//  known position (minus the frame's integer offset); if it is cut by the image border the spot is None in this
+//  frame; otherwise the new position is the python-2-rounded centre of mass of the window (scipy
+//  center_of_mass: integer sums, one float64 division per axis); a position whose size x size square leaves the
+//  image is None (Spot.__init__ raises AttributeError, :100-118); if pflib.illumina_s_n of the new square is below
+//  the cut-off the spot stays where it was (:1244-1250 -- at the PRIOR coordinates, not offset-adjusted, as the
+//  reference does).  A None leaves the last known position in force (:1313-1314).
+//  state: 0 None, 1 centroid accepted, 2 fell back to the prior position, 3 the initial spot (frame 0).
+__global__ void __launch_bounds__(128)
+track_centroid_kernel(const void* __restrict__ frames, int dtype, int n_frames, int H, int W,
+                      const int32_t* __restrict__ spots_hw, const int32_t* __restrict__ spot_field,
+                      const int32_t* __restrict__ offsets, long long n, int size, int R, double cutoff,
+                      int32_t* __restrict__ track_hw, uint8_t* __restrict__ track_state, double* __restrict__ track_sn) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const int half = (size - 1) / 2;
+    const int D = 2 * R + 1;
+    const size_t field_base = (size_t)(spot_field ? spot_field[i] : 0) * n_frames * H * W;
+    int ph = spots_hw[2 * i], pw = spots_hw[2 * i + 1];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int f = 0; f < n_frames; ++f) {
+        const size_t fbase = field_base + (size_t)f * H * W;
+        int nh = ph, nw = pw, state = 3;
+        bool none = false;
+        if (f > 0) {
+            const int oh = ph - (offsets ? offsets[2 * f] : 0), ow = pw - (offsets ? offsets[2 * f + 1] : 0);
+            if (oh - R < 0 || oh + R + 1 > H || ow - R < 0 || ow + R + 1 > W) none = true;          // :1227-1229
+            else {
+                long long S = 0, Sh = 0, Sw = 0;
+                for (int q = lane; q < D * D; q += 32) {
+                    const int r = q / D, c = q - r * D;
+                    const long long v = load_pix_i(frames, dtype, fbase + (size_t)(oh - R + r) * W + (ow - R + c));
+                    S += v; Sh += v * r; Sw += v * c;
+                }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    S += __shfl_xor_sync(0xffffffffu, S, m);
+                    Sh += __shfl_xor_sync(0xffffffffu, Sh, m);
+                    Sw += __shfl_xor_sync(0xffffffffu, Sw, m);
+                }
+                if (S == 0) none = true;            // (the reference divides by zero here and fails in round())
+                else {
+                    const double ch = __ddiv_rn((double)Sh, (double)S), cw = __ddiv_rn((double)Sw, (double)S);
+                    nh = (int)round(__dadd_rn(__dadd_rn(ch, (double)oh), -(double)R));               // :1233-1234
+                    nw = (int)round(__dadd_rn(__dadd_rn(cw, (double)ow), -(double)R));
+                    state = 1;
+                }
+            }
+        }
+        if (!none && !(0 <= nh - half && nh + half < H && 0 <= nw - half && nw + half < W)) none = true;   // Spot.__init__
+        double sn = nan;
+        if (!none) {
+            // pflib.illumina_s_n of the size x size square (pflib.py:261-281): numpy's mean / std arithmetic
+            int v = 0;
+            bool edge = false;
+            if (lane < size * size) {
+                const int r = lane / size, c = lane - r * size;
+                v = load_pix_i(frames, dtype, fbase + (size_t)(nh - half + r) * W + (nw - half + c));
+                edge = (r == 0 || r == size - 1 || c == 0 || c == size - 1);
+            }
+            int mx = lane < size * size ? v : (-2147483647 - 1);
+            long long es = edge ? v : 0;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+                es += __shfl_xor_sync(0xffffffffu, es, m);
+            }
+            const int ne = 4 * (size - 1);
+            const double mean = __ddiv_rn((double)es, (double)ne);
+            // squared deviations summed in numpy's order over the reference's element list: top row, bottom row,
+            // then the (h, 0), (h, -1) pairs of the middle rows (pflib.py:278-280); ne <= 16
+            const double dev = (double)v - mean;
+            const double sq = __dmul_rn(dev, dev);
+            double ordered[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                int src;
+                if (k < size) src = k;
+                else if (k < 2 * size) src = (size - 1) * size + (k - size);
+                else { const int kk = k - 2 * size; src = (1 + kk / 2) * size + ((kk & 1) ? size - 1 : 0); }
+                ordered[k] = __shfl_sync(0xffffffffu, sq, src & 31);
+            }
+            const double var_sum = np_sum(ne, [&](int k) { return ordered[k]; });
+            const double sd = sqrt(__ddiv_rn(var_sum, (double)ne));
+            sn = __ddiv_rn((double)mx - mean, sd);
+            if (f > 0 && sn < cutoff) { nh = ph; nw = pw; state = 2; }                          // :1244-1250
+        }
+        if (lane == 0) {
+            const long long o = i * n_frames + f;
+            track_hw[2 * o] = none ? -1 : nh; track_hw[2 * o + 1] = none ? -1 : nw;
+            track_state[o] = none ? 0 : (uint8_t)state;
+            track_sn[o] = sn;
+        }
+        if (!none) { ph = nh; pw = nw; }
     }
 }
 
@@ -356,6 +434,24 @@ extern "C" int fsq_moments(const void* windows, int dtype_code, int64_t n, int w
     if (lo && !(hi && lim_lo && lim_hi)) { set_error("fsq_moments: lo, hi, lim_lo, lim_hi go together"); return FSQ_E_ARG; }
     moments_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(windows, dtype_code, n, win, p0_out,
                                                                              lo, hi, lim_lo, lim_hi);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
+
+extern "C" int fsq_track_centroid(const void* frames, int dtype_code, int n_fields, int n_frames, int H, int W,
+                                  const int32_t* spots_hw, const int32_t* spot_field, const int32_t* offsets, int64_t n,
+                                  int spot_size, int search_radius, double s_n_cutoff,
+                                  int32_t* track_hw, uint8_t* track_state, double* track_sn, void* stream) {
+    if (n < 0 || n_fields <= 0 || n_frames <= 0 || H <= 0 || W <= 0) { set_error("fsq_track_centroid: bad sizes"); return FSQ_E_ARG; }
+    if (n == 0) return FSQ_OK;
+    if (!frames || !spots_hw || !track_hw || !track_state || !track_sn) { set_error("fsq_track_centroid: NULL pointer argument"); return FSQ_E_ARG; }
+    if (spot_size % 2 == 0) { set_error("Spot.size must be odd."); return FSQ_E_ARG; }                      // flexlibrary.py:98-99
+    if (spot_size < 3 || spot_size > 5) { set_error("fsq_track_centroid: spot_size must be 3 or 5 (got %d)", spot_size); return FSQ_E_ARG; }
+    if (search_radius < 1 || search_radius > 15) { set_error("fsq_track_centroid: search_radius must be in 1..15 (got %d)", search_radius); return FSQ_E_ARG; }
+    if (dtype_code < FSQ_U8 || dtype_code > FSQ_I32) { set_error("fsq_track_centroid: unsupported dtype code %d", dtype_code); return FSQ_E_ARG; }
+    track_centroid_kernel<<<(unsigned)((n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        frames, dtype_code, n_frames, H, W, spots_hw, spot_field, offsets, (long long)n, spot_size, search_radius, s_n_cutoff,
+        track_hw, track_state, track_sn);
     FSQ_LAUNCH_CHECK();
     return FSQ_OK;
 }

@@ -54,4 +54,27 @@ __device__ __forceinline__ int group_bcast_i(int v, int src, unsigned mask) {
     return __shfl_sync(mask, v, src, G);
 }
 
+// numpy's add.reduce over a contiguous run of n < 128 doubles (pairwise_sum: eight strided accumulators, their
+// tree sum, then the remainder in sequence; plain sequence below 8 elements), with no FMA contraction
+template <class F>
+__device__ __forceinline__ double np_sum(int n, F f) {         // numpy pairwise_sum for n < 128
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, f(i));
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f(j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, f(i));
+    return res;
+}
+
 }  // namespace fsq

@@ -40,6 +40,13 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _dev_i32(a, dev):
+    """numpy / list / torch (any device) -> contiguous int32 CUDA tensor"""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.int32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.int32))).to(dev)
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("fluorosequencingimageanalysis_b200 needs a CUDA device (B200, sm_100a); "
@@ -423,8 +430,8 @@ def photometry_batch(frames, spots_hw, spot_frame, method="mexican_hat", radius=
         raise ValueError("Uknown method specified.")                         # flexlibrary.py:315
     if radius is None:
         radius = {"simple": (size - 1) // 2, "mexican_hat": 9, "maximum": 5}[method]
-    hw = torch.as_tensor(np.ascontiguousarray(np.asarray(spots_hw, dtype=np.int32))).to(dev).reshape(-1, 2)
-    fr = torch.as_tensor(np.ascontiguousarray(np.asarray(spot_frame, dtype=np.int32))).to(dev).reshape(-1)
+    hw = _dev_i32(spots_hw, dev).reshape(-1, 2)
+    fr = _dev_i32(spot_frame, dev).reshape(-1)
     out = torch.empty(hw.shape[0], dtype=torch.float64, device=dev)
     _lib.check(L.fsq_photometry(_ptr(frames), _TORCH_DTYPE_CODE[frames.dtype], F, H, W, _ptr(hw), _ptr(fr),
                                 hw.shape[0], PHOT_METHODS[method], int(radius), int(brim_size), _ptr(out),
@@ -442,6 +449,82 @@ def photometry_from_fit(fit, method="gaussian_volume", scaling=10 ** 6):
     if method == "sigmas":
         return float(scaling) * sh * sw
     raise ValueError("Uknown method specified.")                             # flexlibrary.py:315
+
+
+TRACK_NONE, TRACK_CENTROID, TRACK_STAYED, TRACK_INITIAL = 0, 1, 2, 3        # track_state codes of fsq_track_centroid
+
+
+def track_centroid_batch(frames, spots_hw, spot_field=None, offsets=None, size=5, search_radius=3, s_n_cutoff=3.0):
+    """Experiment.luminosity_centroid_particle_tracking (flexlibrary.py:1262-1317) for n spots of frame 0.
+    frames [n_frames,H,W] (one field) or [n_fields,n_frames,H,W]; spots_hw [n,2]; spot_field [n] for several
+    fields; offsets [n_frames,2] integer (delta_h, delta_w) or None.
+    -> (track_hw [n,n_frames,2] i32, track_state [n,n_frames] u8, track_sn [n,n_frames] f64) device tensors."""
+    L = _lib.load()
+    require_cuda()
+    if size % 2 == 0:
+        raise AttributeError("Spot.size must be odd.")                       # flexlibrary.py:98-99
+    if isinstance(frames, np.ndarray) and frames.ndim == 4:
+        nf = frames.shape[0]
+        fr = to_device_frames(frames.reshape((-1,) + frames.shape[2:]))
+        fr = fr.reshape((nf, -1) + tuple(fr.shape[1:]))
+    elif isinstance(frames, torch.Tensor) and frames.dim() == 4:
+        fr = frames.contiguous()
+        if fr.dtype not in _TORCH_DTYPE_CODE or fr.dtype in (torch.float64, torch.int64):
+            raise TypeError("unsupported frame dtype %s" % fr.dtype)
+    else:
+        fr = to_device_frames(frames).unsqueeze(0)
+    n_fields, n_frames, H, W = fr.shape
+    dev = fr.device
+    hw = _dev_i32(spots_hw, dev).reshape(-1, 2)
+    n = hw.shape[0]
+    sf = None
+    if spot_field is not None:
+        sf = _dev_i32(spot_field, dev).reshape(-1)
+        if sf.numel() != n or (n and (int(sf.min()) < 0 or int(sf.max()) >= n_fields)):
+            raise ValueError("spot_field must hold one field index in [0, n_fields) per spot")
+    elif n_fields != 1:
+        raise ValueError("spot_field is required when frames holds several fields")
+    of = None
+    if offsets is not None:
+        o = np.asarray(offsets)
+        if o.shape != (n_frames, 2) or not np.all(o == np.rint(o)):
+            raise ValueError("offsets must be integer (delta_h, delta_w) pairs, one per frame")
+        of = torch.as_tensor(np.ascontiguousarray(o.astype(np.int32))).to(dev)
+    track_hw = torch.empty((n, n_frames, 2), dtype=torch.int32, device=dev)
+    track_state = torch.empty((n, n_frames), dtype=torch.uint8, device=dev)
+    track_sn = torch.empty((n, n_frames), dtype=torch.float64, device=dev)
+    _lib.check(L.fsq_track_centroid(_ptr(fr), _TORCH_DTYPE_CODE[fr.dtype], n_fields, n_frames, H, W, _ptr(hw), _ptr(sf),
+                                    _ptr(of), n, int(size), int(search_radius), float(s_n_cutoff), _ptr(track_hw),
+                                    _ptr(track_state), _ptr(track_sn), _stream()))
+    return track_hw, track_state, track_sn
+
+
+def timetrace_batch(frames, faithful=False, solver="fast", r_2_threshold=0.7, consolidation_radius=4,
+                    search_radius=3, s_n_cutoff=3.0, photometry_method="mexican_hat", **photometry_kw):
+    """The device part of basic_timetrace_script.py for one field's movie [n_frames,H,W]: frame 0
+    is peak-fitted (find_peptides), its final PSFs are followed through the frames by the luminosity centroid
+    (lc_create_traces), and Spot.photometry is evaluated for every (spot, frame) (stepfit_tracks' input).
+    -> dict(psf_int [m,4], psf_fit [m,12], track_hw [m,F,2], track_state [m,F], track_sn [m,F], photometry [m,F])
+    as numpy arrays; photometry is NaN where the spot is None."""
+    frames = to_device_frames(frames)
+    F = frames.shape[0]
+    res = find_peptides_batch(frames[:1], faithful=faithful, solver=solver, to_host=False)
+    n = int(res.cand_hw.shape[0])
+    cons = consolidate_batch(res.cand_hw, res.cand_frame, res.fit, n, 1, r_2_threshold, consolidation_radius)
+    cons.check()
+    pk = pack_psfs_batch(cons, res.cand_frame, res.fit, n, 1)
+    m = int(pk.base[1].item())
+    psf_int, psf_fit = pk.ints[:m], pk.fit[:m]
+    spots = psf_int[:, 1:3].contiguous()
+    thw, tst, tsn = track_centroid_batch(frames, spots, search_radius=search_radius, s_n_cutoff=s_n_cutoff)
+    live = tst.reshape(-1) != TRACK_NONE
+    hw_flat = thw.reshape(-1, 2)
+    fr_idx = torch.arange(F, dtype=torch.int32, device=frames.device).repeat(m)
+    phot = torch.full((m * F,), float("nan"), dtype=torch.float64, device=frames.device)
+    if int(live.sum()):
+        phot[live] = photometry_batch(frames, hw_flat[live], fr_idx[live], method=photometry_method, **photometry_kw)
+    return {"psf_int": psf_int.cpu().numpy(), "psf_fit": psf_fit.cpu().numpy(), "track_hw": thw.cpu().numpy(),
+            "track_state": tst.cpu().numpy(), "track_sn": tsn.cpu().numpy(), "photometry": phot.reshape(m, F).cpu().numpy()}
 
 
 class FieldResults(object):

@@ -238,6 +238,26 @@ int fsq_pack_psfs(const uint8_t* psf_state, const int32_t* psf_key, const int32_
                   double* psf_fit, int32_t* psf_int, int64_t* psf_base, int64_t cap_psf,
                   void* scratch, int64_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Luminosity-centroid particle tracking -- replaces Experiment.luminosity_centroid_particle_tracking and
+ * next_frame_spot_by_luminosity_centroid (flexlibrary.py:1173-1317), the tracker of the time-trace path
+ * (basic_timetrace_script.py -> TimetraceExperiment.lc_create_traces, flexlibrary.py:3309-3382), for n
+ * spots of frame 0 through the n_frames frames of their field.
+ *   in   frames [n_fields, n_frames, H, W]; spots_hw [n,2] i32 positions in frame 0; spot_field [n] i32
+ *        (NULL: one field); offsets [n_frames,2] i32 per-frame (delta_h, delta_w) (NULL: none; the
+ *        reference's caller passes None); spot_size (Spot.size, 3 or 5), search_radius (3), s_n_cutoff (3.0)
+ *   out  track_hw [n, n_frames, 2] i32   the spot's pixel in every frame, (-1, -1) where the reference has None
+ *        track_state [n, n_frames] u8    0 None (window or spot square cut by the border), 1 centroid accepted,
+ *                                        2 Illumina S/N below the cut-off: stays at the prior position, 3 frame 0
+ *        track_sn [n, n_frames] f64      pflib.illumina_s_n of the square at the centroid position (NaN for None)
+ * Integer pixel sums; centre of mass = one float64 division per axis (scipy center_of_mass); python-2 round().
+ * A window whose pixels are all zero gives None (the reference divides by zero and raises there).
+ * ------------------------------------------------------------------------------------------ */
+int fsq_track_centroid(const void* frames, int dtype_code, int n_fields, int n_frames, int H, int W,
+                       const int32_t* spots_hw, const int32_t* spot_field, const int32_t* offsets, int64_t n,
+                       int spot_size, int search_radius, double s_n_cutoff,
+                       int32_t* track_hw, uint8_t* track_state, double* track_sn, void* stream);
+
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);

@@ -277,3 +277,29 @@ def test_read_image_png_and_conversion(tmp_path):
     assert conv2 == conv and np.array_equal(back2, img)
     with pytest.raises(Exception):
         pflib.read_image(str(tmp_path / "missing.tif"))
+
+
+# ------------------------------------------------------------------ tracking oracle (restated by reading)
+def test_track_oracle_known_answers():
+    """Hand-checkable cases of the luminosity-centroid tracker's restatement (flexlibrary.py:1173-1317): the
+    centroid follows a bright pixel, python-2 rounding at .5, None at the border, fall-back below the S/N cut-off."""
+    from oracle import track_oracle as tro
+    H = W = 20
+    f0 = np.full((H, W), 10, dtype=np.uint16)
+    f1 = f0.copy(); f1[9, 11] = 60000                       # one very bright pixel: the 7x7 centre of mass lands next to it
+    f2 = f0.copy()                                          # flat: std = 0 -> S/N = nan -> `nan < cutoff` is False -> centroid kept
+    hw, st, sn = tro.track([f0, f1, f2], [(10, 10)])
+    assert hw[0].tolist() == [[10, 10], [9, 11], [9, 11]] and st[0].tolist() == [3, 1, 1]
+    assert np.isnan(sn[0, 2]) and sn[0, 1] > 3
+    # window cut by the border -> None; the last known position stays in force for the next frame
+    hw, st, _ = tro.track([f0, f0, f1], [(2, 2)])
+    assert st[0].tolist() == [3, 0, 0] and hw[0, 1].tolist() == [-1, -1]
+    # S/N below the cut-off -> the spot stays at the prior position (state 2)
+    g = f0.copy(); g[10, 10] = 12; g[8, 8] = 11             # weak, with an uneven border so that std > 0
+    hw, st, sn = tro.track([f0, g], [(10, 10)], s_n_cutoff=50.0)
+    assert st[0, 1] == 2 and hw[0, 1].tolist() == [10, 10] and sn[0, 1] < 50
+    # an even Spot.size is refused like the reference does (flexlibrary.py:98-99)
+    with pytest.raises(AttributeError):
+        tro.make_spot((H, W), 10, 10, 4)
+    with pytest.raises(AttributeError):
+        tro.make_spot((H, W), 1, 10, 5)                     # the 5x5 square leaves the image
