@@ -91,3 +91,13 @@ def cut_windows(frame, cr, cc, win=11):
             continue
         out.append(frame[ri - h:ri + h + 1, ci - h:ci + h + 1].astype(np.float64))
     return np.stack(out)
+
+
+def shifted_pair(seed, H, W, dy, dx, n_spots, sigma=1.5, bg=400.0):
+    """Two frames of one spot layout, the second drifted by a sub-pixel (dy, dx), independent noise
+    (registration test input: phase_correlate)."""
+    _, cr, cc, amp = spot_layout(seed, H, W, n_spots)
+    a = add_noise(render_clean(cr, cc, amp, H, W, sigma, bg), np.random.default_rng(100 + seed))
+    cr2, cc2 = np.clip(cr + dy, 8, H - 8), np.clip(cc + dx, 8, W - 8)
+    b = add_noise(render_clean(cr2, cc2, amp, H, W, sigma, bg), np.random.default_rng(200 + seed))
+    return a, b

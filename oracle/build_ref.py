@@ -8,6 +8,7 @@ transliteration of the three reference files that hold the hot path
     /root/reference/agpy/mpfit/mpfit.py      (MINPACK-1 LM solver, class mpfit)
     /root/reference/agpy/gaussfitter.py      (lines 1-255: moments/twodgaussian/gaussfit)
     /root/reference/pflib.py                 (_psf_candidates, _fit_2d_gaussian, find_peptides ...)
+    /root/reference/phase_correlate.py       (frame registration; one numpy-2 API rewrite)
 
 The reference is Python 2 and does not parse under the Python 3.12 of this
 image.  This script plays the role a
@@ -125,8 +126,16 @@ def convert_pflib(src):
     return text[:idx] + "\n" + _PFLIB_HEADER + text[idx:]
 
 
+def convert_phase_correlate(src):
+    # phase_correlate.py is plain numpy and runs unchanged on Python 3 but for one numpy-2 API change:
+    # numpy.array(..., copy=False) now raises when a copy is needed (uint16 -> float64 always needs one)
+    return src.replace("np.array(ref_image, dtype=np.float64, copy=False)", "np.asarray(ref_image, dtype=np.float64)") \
+              .replace("np.array(reg_image, dtype=np.float64, copy=False)", "np.asarray(reg_image, dtype=np.float64)")
+
+
 def build(ref_root="/root/reference", check=False, quiet=False):
     paths = {
+        "phase_correlate": os.path.join(ref_root, "phase_correlate.py"),
         "mpfit": os.path.join(ref_root, "agpy", "mpfit", "mpfit.py"),
         "gaussfitter": os.path.join(ref_root, "agpy", "gaussfitter.py"),
         "pflib": os.path.join(ref_root, "pflib.py"),
@@ -139,6 +148,7 @@ def build(ref_root="/root/reference", check=False, quiet=False):
         "mpfit": convert_mpfit(srcs["mpfit"]),
         "gaussfitter": convert_gaussfitter(srcs["gaussfitter"]),
         "pflib": convert_pflib(srcs["pflib"]),
+        "phase_correlate": convert_phase_correlate(srcs["phase_correlate"]),
     }
     if check:
         for k in conv:
@@ -158,8 +168,10 @@ def build(ref_root="/root/reference", check=False, quiet=False):
         f.write(conv["gaussfitter"])
     with open(os.path.join(OUT, "pflib.py"), "w") as f:
         f.write(conv["pflib"])
+    with open(os.path.join(OUT, "phase_correlate.py"), "w") as f:
+        f.write(conv["phase_correlate"])
     # compile check: every output must parse
-    for rel in ("agpy/mpfit/mpfit.py", "gaussfitter.py", "pflib.py"):
+    for rel in ("agpy/mpfit/mpfit.py", "gaussfitter.py", "pflib.py", "phase_correlate.py"):
         p = os.path.join(OUT, rel)
         compile(open(p).read(), p, "exec")
     if not quiet:
@@ -191,6 +203,18 @@ def load():
                 sys.modules.pop(k, None)
         if OUT in sys.path:
             sys.path.remove(OUT)
+
+
+def load_phase_correlate():
+    """The reference's phase_correlate module (phase_correlate.py:11-196) from oracle/_ref, or None."""
+    path = os.path.join(OUT, "phase_correlate.py")
+    if not os.path.isfile(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_phase_correlate", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 if __name__ == "__main__":

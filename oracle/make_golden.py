@@ -231,3 +231,23 @@ if __name__ == "__main__":
         make_fits11(a.procs)
     if "fits5" in todo:
         make_fits5(a.procs)
+
+
+# ----------------------------------------------------------------------------- phase_correlate (reference run)
+PHASE_CASES = [(1, 256, 256, 0.0, 0.0, 150), (2, 256, 256, 2.0, -3.0, 150), (3, 256, 256, 0.35, -1.6, 150),
+               (4, 200, 333, -1.25, 0.8, 200), (5, 512, 512, 0.45, 0.15, 500), (6, 128, 96, 3.7, 2.2, 60)]
+
+
+def make_phase_correlate_golden(path):
+    """tests/golden/phase_correlate.npz: outputs of the reference's own phase_correlate (oracle/_ref, built from
+    /root/reference/phase_correlate.py) on synth.shifted_pair inputs, upsample_factor 1 and 20."""
+    import numpy as np
+    from oracle import build_ref
+    from fluorosequencingimageanalysis_b200 import synth
+    m = build_ref.load_phase_correlate()
+    out1, out20 = [], []
+    for seed, H, W, dy, dx, n in PHASE_CASES:
+        a, b = synth.shifted_pair(seed, H, W, dy, dx, n)
+        out1.append([float(np.real(v)) for v in m.phase_correlate(a, b, 1)])
+        out20.append([float(np.real(v)) for v in m.phase_correlate(a, b, 20)])
+    np.savez_compressed(path, cases=np.array(PHASE_CASES, dtype=float), out1=np.array(out1), out20=np.array(out20))

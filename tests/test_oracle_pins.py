@@ -131,3 +131,20 @@ def test_oracle_bitwise_equals_reference_live(frame0, fits5):
         mine = po.fit_2d_gaussian(sub, faithful=True)
         for a, b in zip(ref, mine):
             assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_phase_correlate_golden_is_the_reference_output():
+    """tests/golden/phase_correlate.npz was written by the reference's own phase_correlate.py (oracle/_ref); where
+    oracle/_ref exists the run is repeated and must reproduce the file bit for bit."""
+    from oracle import build_ref
+    from fluorosequencingimageanalysis_b200 import synth
+    m = build_ref.load_phase_correlate()
+    if m is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    g = golden("phase_correlate.npz")
+    for k, (seed, H, W, dy, dx, n) in enumerate(g["cases"]):
+        a, b = synth.shifted_pair(int(seed), int(H), int(W), dy, dx, int(n))
+        assert [float(np.real(v)) for v in m.phase_correlate(a, b, 1)] == g["out1"][k].tolist()
+        assert [float(np.real(v)) for v in m.phase_correlate(a, b, 20)] == g["out20"][k].tolist()
+    # sub-pixel drifts come back at the 1/20 px resolution the caller asks for (flexlibrary.py:1717)
+    assert g["out20"][2][:2].tolist() == [-0.35, 1.6] and g["out20"][4][:2].tolist() == [-0.45, -0.15]
