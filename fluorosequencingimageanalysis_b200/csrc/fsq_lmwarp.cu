@@ -408,7 +408,10 @@ lmwarp_kernel(const WarpArgs a) {
 
     // (Claiming one slot ahead per lane and prefetching its start record was measured on B200: it hides the two
     //  round trips of a refill but a lane inside a 200-iteration fit then sits on an unstarted candidate, and the
-    //  40-frame launch got 10 % SLOWER (1.65 -> 1.82 ms); the queue stays strictly on demand.)
+    //  40-frame launch got 10 % SLOWER (1.65 -> 1.82 ms).  A warp-level pool with guided claim sizes (up to 32
+    //  candidates per atomic, records prefetched, claims shrinking to 1 towards the end of the queue) avoids that
+    //  imbalance and measured no gain either (1.86 vs 1.78 ms; 160 frames and the pipelined step unchanged): the
+    //  refill's round trips are hidden by the other resident warps.  The queue stays strictly on demand.)
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         __syncwarp();
@@ -561,26 +564,23 @@ lmwarp_kernel(const WarpArgs a) {
                 // ---------------------------------------------------------- new linearisation at x
                 rss0 = __fdividef(1.0f, (float)ss0);
                 // pegged parameters: zero the column when the gradient pushes outwards (:1073-1091)
+                // (a zeroed column is not multiplied out of the 28 accumulators: its diagonal is read as 0 here and
+                //  its scale factor as 0 in the store below, which leaves the same numbers in shared memory)
                 lpeg = 0; upeg = 0;
+                float acn[WNP], iSz[WNP];
+                float gmax = 0.0f;
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) {
                     const bool lp = lim.has_lo(j) && (x[j] == lim.lower(j));
                     const bool up = lim.has_hi(j) && (x[j] == lim.upper(j));
                     lpeg |= (lp ? 1u : 0u) << j; upeg |= (up ? 1u : 0u) << j;
                     const bool zero = (lp && gn[j] > 0.0f) || (up && gn[j] < 0.0f);
-                    const float keep = zero ? 0.0f : 1.0f;
-                    gn[j] *= keep;
-#pragma unroll
-                    for (int k = 0; k < WNP; ++k) An[(k >= j) ? wtri(k, j) : wtri(j, k)] *= keep;
-                }
-                float acn[WNP];
-                float gmax = 0.0f;
-#pragma unroll
-                for (int j = 0; j < WNP; ++j) {
-                    const float ajj = An[wtri(j, j)];
+                    gn[j] = zero ? gn[j] * 0.0f : gn[j];
+                    const float ajj = zero ? An[wtri(j, j)] * 0.0f : An[wtri(j, j)];
                     const float rs = ajj > 0.0f ? rsqrtf(ajj) : 0.0f;
                     acn[j] = ajj * rs;                                                   // column norms (:1758)
                     iS[j] = ajj > 0.0f ? rs : 1.0f;
+                    iSz[j] = zero ? 0.0f : iS[j];
                     gn[j] *= iS[j];                                                      // scaled gradient
                     if (ajj > 0.0f) gmax = fmaxf(gmax, fabsf(gn[j]));                    // :1142-1148
                 }
@@ -604,7 +604,7 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
                 for (int i = 0; i < WNP; ++i) {
 #pragma unroll
-                    for (int k = 0; k <= i; ++k) sA[wtri(i, k) * TPB] = An[wtri(i, k)] * (iS[i] * iS[k]);
+                    for (int k = 0; k <= i; ++k) sA[wtri(i, k) * TPB] = An[wtri(i, k)] * (iSz[i] * iSz[k]);
                     sg[i * TPB] = gn[i];
                 }
             }
