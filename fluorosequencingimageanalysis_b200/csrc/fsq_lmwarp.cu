@@ -256,7 +256,12 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     const double Hh = pt[0], Aa = pt[1];
     double sn, cs;
     w_sincos_deg(pt[6], &sn, &cs);                                            // gaussfitter.py:115
-    const double iwx = 1.0 / pt[4], iwy = 1.0 / pt[5];
+    // A width sitting exactly on a lower limit of 0 (gaussfit's default limits, gaussfitter.py:143-146): the reference
+    // divides the finite rotated offset by it, gets +-inf, and exp(-inf) = 0 leaves the flat model H.  Pre-multiplied
+    // reciprocals would give inf - inf = NaN here, so the generic entry maps that case to E = 0 explicitly.
+    const bool flat = CLAMP && ((pt[4] == 0.0) || (pt[5] == 0.0));
+    const double ezero = flat ? 0.0 : 1.0;
+    const double iwx = (CLAMP && pt[4] == 0.0) ? 0.0 : 1.0 / pt[4], iwy = (CLAMP && pt[5] == 0.0) ? 0.0 : 1.0 / pt[5];
     const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
     // per-column terms of the rotated offsets (numpy.indices: y = column index pairs with p[2]);
     // 5x5: tables in registers; larger windows: one multiply-add per pixel instead
@@ -320,7 +325,8 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
             float af, bf;
             if (RECUR) {
                 av = 0.0; bv = 0.0;
-                af = raf - caf[c]; bf = rbf + cbf[c];
+                if (TABLES) { af = raf - caf[c]; bf = rbf + cbf[c]; }
+                else { const float dyf = cyf - (float)c; af = fmaf(-dyf, sx, raf); bf = fmaf(dyf, cyw, rbf); }
             } else if (TABLES) {
                 av = ra - ca[c]; bv = rb + cb[c];
                 af = raf - caf[c]; bf = rbf + cbf[c];
@@ -332,7 +338,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
             }
             double E;
             if (RECUR) { E = Ec; Ec *= Gc; Gc *= Kc; }
-            else E = w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
+            else E = CLAMP ? ezero * w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av)) : w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
             const double f = drow[c * TPB] - fma(Aa, E, Hh);
             ss = fma(f, f, ss);
             const float Ef = (float)E, ff = (float)f;

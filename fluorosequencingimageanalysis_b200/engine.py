@@ -188,8 +188,13 @@ class FitBatch(object):
 
 
 def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perror=False,
-                   want_fit_img=False, opts=None, solver="minpack", **mpfit_kw):
-    """gaussfitter.gaussfit -> mpfit (agpy/gaussfitter.py:142-255) for n windows [n,win,win]."""
+                   want_fit_img=False, opts=None, solver="minpack", rescue=None, **mpfit_kw):
+    """gaussfitter.gaussfit -> mpfit (agpy/gaussfitter.py:142-255) for n windows [n,win,win].
+
+    ``rescue`` (default: on for solver="fast"): the FAST solver keeps its normal equations in FP32 and reports
+    status -16 when they leave the finite range (measured: 0.03 % of 11x11 windows cut from a dense field, fits
+    that chase a neighbour's tail 10 px outside the window); those fits are re-run by the reference-faithful
+    FP64 MINPACK kernel -- on the device, like everything else -- and their rows replaced."""
     L = _lib.load()
     require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -234,6 +239,17 @@ def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perr
                               _ptr(r.status), _ptr(r.niter), _ptr(r.nfev), _ptr(r.chi2), _ptr(r.n_qrsolv),
                               _ptr(r.fit_img), _ptr(counter), _stream())
     _lib.check(rc)
+    if rescue is None:
+        rescue = (solver == "fast" and opts is None)
+    if rescue and solver == "fast" and n:
+        bad = torch.nonzero(r.status == -16).reshape(-1)
+        if bad.numel():
+            rr = gaussfit_batch(w[bad], p0[bad], lo[bad], hi[bad], lim_lo[bad], lim_hi[bad], faithful=faithful,
+                                want_fit_img=want_fit_img, solver="minpack", rescue=False, **mpfit_kw)
+            for name in ("params", "status", "niter", "nfev", "chi2", "n_qrsolv", "fit_img"):
+                dst, src = getattr(r, name), getattr(rr, name)
+                if dst is not None and src is not None:
+                    dst[bad] = src
     return r
 
 

@@ -274,6 +274,35 @@ def test_fast_generic_edge_cases():
         engine.gaussfit_batch(np.zeros((1, 7, 7)), p0[:1], lo[:1], hi[:1], lmin[:1], lmax[:1], solver="fast")
 
 
+def test_fast_11x11_dense_field_windows_with_widths_on_the_zero_limit():
+    """BASELINE configs[3]: 11x11 windows cut from a dense frame hold several spots; with gaussfit's default limits a
+    width then runs onto its lower limit 0, where the reference's model degenerates to the flat height (division by
+    zero -> inf -> exp(-inf) = 0).  The FAST generic entry must carry on like the reference-faithful solver does:
+    every fit ends with a convergence status, and the chi^2 is not worse on the bulk."""
+    engine, _, synth, _ = _mods()
+    fr = synth.synth_frame(40, H=1024, W=1024, n_spots=5000)
+    _, cr, cc, _ = synth.spot_layout(40, 1024, 1024, 5000)
+    r0, c0 = np.rint(cr).astype(int), np.rint(cc).astype(int)
+    win = np.stack([fr[a - 5:a + 6, b - 5:b + 6] for a, b in zip(r0, c0)]).astype(np.float64)
+    rf, p0 = engine.gaussfit_default_batch(win, solver="fast", faithful=False)
+    rm, _ = engine.gaussfit_default_batch(win, solver="minpack", faithful=False)
+    sf, sm = rf.status.cpu().numpy(), rm.status.cpu().numpy()
+    zero_w = (rm.params.cpu().numpy()[:, 4:6] == 0).any(axis=1)
+    print("dense 11x11: %d windows, %d end with a width on the 0 limit (MINPACK); FAST status<=0: %d" % (len(sf), zero_w.sum(), (sf <= 0).sum()))
+    assert zero_w.sum() > 10                                   # the case is exercised
+    assert (sm > 0).all() and (sf > 0).all()
+    # without the FP64 rescue of non-finite FAST fits (engine.gaussfit_batch) a handful report -16, never silently
+    lo, hi, lmin, lmax = engine.GAUSSFIT_DEFAULT_LIMITS
+    n = len(win)
+    raw = engine.gaussfit_batch(win, p0, np.tile(lo, (n, 1)), np.tile(hi, (n, 1)), np.tile(lmin, (n, 1)), np.tile(lmax, (n, 1)),
+                                solver="fast", faithful=False, rescue=False)
+    sr = raw.status.cpu().numpy()
+    print("FAST without rescue: %d of %d fits report -16" % ((sr == -16).sum(), n))
+    assert ((sr > 0) | (sr == -16)).all() and (sr == -16).mean() < 0.002
+    cf, cm = rf.chi2.cpu().numpy(), rm.chi2.cpu().numpy()
+    assert np.mean(cf <= cm * (1 + 1e-6)) > 0.95
+
+
 # ------------------------------------------------------------------------------------ BASELINE configs 3 / 4 shapes
 def test_config4_dense_2048_frame_properties():
     """BASELINE configs[3]: one 2048x2048 frame at high density (20 000 spots, overlaps present).  The CPU
