@@ -515,6 +515,77 @@ def track_centroid_batch(frames, spots_hw, spot_field=None, offsets=None, size=5
     return track_hw, track_state, track_sn
 
 
+def accumulate_offsets(offsets):
+    """Experiment.accumulate_offsets (flexlibrary.py:566-593): Python sums, in sequence."""
+    if tuple(offsets[0]) != (0, 0):
+        raise ValueError("The first image's offset must be (0, 0) by definiton.")
+    return [(sum([o[0] for o in offsets[:f + 1]]), sum([o[1] for o in offsets[:f + 1]])) for f in range(len(offsets))]
+
+
+def track_greedy_batch(field_frame_spots, frame_shape, candidate_radius=2, offsets=None, spot_radius=0):
+    """Experiment.greedy_particle_tracking (flexlibrary.py:680-1027) for several fields in one launch.
+    field_frame_spots: per field a list (frames) of [k,2] arrays / lists of (h, w) -- or one such list of frames for
+    a single field; offsets: per field a list of per-frame (delta_h, delta_w), or one list for all, or None.
+    -> per field (traces [n_traces, n_frames] int64: the spot's index in its frame's list or -1 for None, in the
+    reference's order of traces; total_discarded) -- a bare tuple when one field was given."""
+    L = _lib.load()
+    require_cuda()
+    single = len(field_frame_spots) > 0 and (len(field_frame_spots[0]) == 0 or np.ndim(field_frame_spots[0][0]) < 2)
+    fields = [field_frame_spots] if single else list(field_frame_spots)
+    n_fields = len(fields)
+    F = len(fields[0])
+    if any(len(fr) != F for fr in fields):
+        raise ValueError("every field must have the same number of frames")
+    H, W = int(frame_shape[0]), int(frame_shape[1])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if offsets is None:
+        cum = None
+    else:
+        per_field = offsets if (n_fields > 1 and np.ndim(offsets) == 3) else [offsets] * n_fields
+        cum = np.array([accumulate_offsets([tuple(o) for o in off]) for off in per_field], dtype=np.float64).reshape(n_fields, F, 2)
+    seg, pts = [0], []
+    for fr in fields:
+        for sp in fr:
+            a = np.asarray(sp, dtype=np.float64).reshape(-1, 2)
+            pts.append(a)
+            seg.append(seg[-1] + len(a))
+    n = seg[-1]
+    hw = torch.from_numpy(np.ascontiguousarray(np.concatenate(pts) if n else np.zeros((0, 2)))).to(dev)
+    seg_t = torch.tensor(seg, dtype=torch.int32, device=dev)
+    cum_t = torch.from_numpy(cum).to(dev) if cum is not None else None
+    anc = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    desc = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    bins = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
+    disc = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    flags = torch.empty(n_fields, dtype=torch.int32, device=dev)
+    sbytes = int(L.fsq_track_greedy_scratch_bytes(n_fields, H, W, n))
+    scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.fsq_track_greedy(_ptr(hw), _ptr(seg_t), _ptr(cum_t), n_fields, F, H, W, n, int(candidate_radius),
+                                  float(spot_radius), _ptr(anc), _ptr(desc), _ptr(bins), _ptr(disc), _ptr(flags),
+                                  _ptr(scratch), sbytes, _stream()))
+    if int((flags & 1).any()):
+        raise AssertionError("two spots of one frame round to the same pixel (flexlibrary.py:853-858)")
+    anc, desc, bins, disc = anc.cpu().numpy()[:n], desc.cpu().numpy()[:n], bins.cpu().numpy()[:n], disc.cpu().numpy()[:n]
+    seg = np.array(seg)
+    frame_of = np.repeat(np.arange(n_fields * F), np.diff(seg))
+    out = []
+    for b in range(n_fields):
+        lo, hi = seg[b * F], seg[(b + 1) * F]
+        idx = np.arange(lo, hi)
+        local_frame = frame_of[lo:hi] - b * F
+        heads = idx[(anc[lo:hi] < 0) & (disc[lo:hi] == 0)]
+        # the reference collects the heads frame by frame, each frame in raster order of the rounded pixels (:986-993)
+        order = np.lexsort((bins[heads, 1], bins[heads, 0], frame_of[heads]))
+        traces = -np.ones((len(heads), F), dtype=np.int64)
+        for t, h in enumerate(heads[order]):
+            cur = h
+            while cur >= 0:
+                traces[t, frame_of[cur] - b * F] = cur - seg[frame_of[cur]]
+                cur = desc[cur]
+        out.append((traces, int(disc[lo:hi].sum())))
+    return out[0] if single else out
+
+
 def timetrace_batch(frames, faithful=False, solver="fast", r_2_threshold=0.7, consolidation_radius=4,
                     search_radius=3, s_n_cutoff=3.0, photometry_method="mexican_hat", **photometry_kw):
     """The device part of basic_timetrace_script.py for one field's movie [n_frames,H,W]: frame 0

@@ -258,6 +258,29 @@ int fsq_track_centroid(const void* frames, int dtype_code, int n_fields, int n_f
                        int spot_size, int search_radius, double s_n_cutoff,
                        int32_t* track_hw, uint8_t* track_state, double* track_sn, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Greedy cross-frame particle tracking -- replaces Experiment.greedy_particle_tracking
+ * (flexlibrary.py:680-1027; drop-outs :626-677, offsets :566-617), the tracker of the experiment path (one
+ * frame per Edman cycle), for the spots of n_fields fields at once.
+ *   in   spot_hw [n,2] f64 (Spot.h, Spot.w), spots sorted by (field, frame); seg_start [n_fields*n_frames+1]
+ *        i32 first spot of every (field, frame); cum_offsets [n_fields, n_frames, 2] f64 = accumulate_offsets
+ *        of the per-frame offsets (NULL: no drift); candidate_radius (2), spot_radius (0)
+ *   out  anc / desc [n] i32  the spot's ancestor / descendant (global spot index, -1 none): the doubly linked
+ *                            lists a_L / d_L of the reference's frame_bins; a trace is a chain from a spot with
+ *                            anc = -1, and may skip frames
+ *        bin_hw [n,2] i32    rounded drift-corrected pixel (python-2 round), (-1,-1) for dropped spots
+ *        discarded [n] u8    1: the spot would leave some frame of the sequence (discard_dropouts)
+ *        flags [n_fields] i32  bit 0: two spots of one frame share a pixel (the reference asserts, :853-858)
+ * The reference sorts all (ancestor, candidate) pairs of a frame by distance (stable sort over ancestors in
+ * raster order, candidates in raster order) and links greedily; the kernel replays that walk exactly in
+ * parallel rounds of mutually-best pairs.  Scratch is two H x W index grids per field.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fsq_track_greedy_scratch_bytes(int n_fields, int H, int W, int64_t n);
+int fsq_track_greedy(const double* spot_hw, const int32_t* seg_start, const double* cum_offsets,
+                     int n_fields, int n_frames, int H, int W, int64_t n, int candidate_radius,
+                     double spot_radius, int32_t* anc, int32_t* desc, int32_t* bin_hw, uint8_t* discarded,
+                     int32_t* flags, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);

@@ -80,3 +80,96 @@ def track(frames, initial_spots, size=5, search_radius=3, s_n_cutoff=3.0, offset
                 hw[i, f] = nxt
                 prior = nxt
     return hw, state, sn
+
+
+# ----------------------------------------------------------------------------- greedy cross-frame tracking
+def accumulate_offsets(offsets):
+    """flexlibrary.py:566-593 (Python sums, in sequence)."""
+    if tuple(offsets[0]) != (0, 0):
+        raise ValueError("The first image's offset must be (0, 0) by definiton.")
+    return [(sum([o[0] for o in offsets[:f + 1]]), sum([o[1] for o in offsets[:f + 1]])) for f in range(len(offsets))]
+
+
+def discard_dropouts(spots, spot_offset, frame_cumulative_offsets, image_shape, spot_radius=0):
+    """flexlibrary.py:626-677 for the spots [(h, w)] of one frame -> (kept indices, number discarded)."""
+    kept, number_discarded = [], 0
+    for i, (h, w) in enumerate(spots):
+        oh, ow = h + spot_offset[0], w + spot_offset[1]
+        for off in frame_cumulative_offsets:
+            gh, gw = oh - off[0], ow - off[1]
+            if not (spot_radius <= gh < image_shape[0] - 0.5 - spot_radius and
+                    spot_radius <= gw < image_shape[1] - 0.5 - spot_radius):
+                number_discarded += 1
+                break
+        else:
+            kept.append(i)
+    return kept, number_discarded
+
+
+def greedy_particle_tracking(frame_spots, frame_shape, candidate_radius=2, offsets=None, spot_radius=0):
+    """flexlibrary.py:680-1027.  frame_spots: per frame a list of (h, w).  Returns (traces, total_discarded) with
+    every trace a list of length n_frames holding the spot's index in its frame's list, or None.
+    The reference's object arrays of dictionaries are restated as dictionaries keyed by the rounded pixel; every
+    loop that walks an array with numpy.ndenumerate walks the keys in raster order here."""
+    from scipy.spatial.distance import euclidean
+    F = len(frame_spots)
+    if offsets is None:
+        offsets = [(0, 0) for _ in range(F)]
+    cum = accumulate_offsets(offsets)
+    H, W = frame_shape
+    total_discarded = 0
+    kept = []
+    for f in range(F):
+        k, nd = discard_dropouts(frame_spots[f], cum[f], cum, frame_shape, spot_radius)
+        kept.append(k)
+        total_discarded += nd
+    bins = [dict() for _ in range(F)]                       # (rh, rw) -> {'spt': index, 'a_L': ..., 'd_L': ...}
+    for f in range(F):
+        for i in kept[f]:
+            h, w = frame_spots[f][i][0] + cum[f][0], frame_spots[f][i][1] + cum[f][1]
+            rh, rw = int(py2_round(h)), int(py2_round(w))
+            assert (rh, rw) not in bins[f], "%s is already filled in frame_bins[%d]" % ((rh, rw), f)
+            bins[f][(rh, rw)] = {'spt': i, 's_L': (f, rh, rw), 'a_L': None, 'd_L': None}
+    cache = {}
+    pos = lambda f, i: (frame_spots[f][i][0] + cum[f][0], frame_spots[f][i][1] + cum[f][1])
+    for f in range(1, F):
+        frame = bins[f]
+        for (rh, rw) in sorted(bins[f - 1]):
+            cache[(rh, rw)] = {'spt': bins[f - 1][(rh, rw)]['spt'], 's_L': (f - 1, rh, rw)}
+        pairs = []
+        for (ah, aw) in sorted(cache):
+            a = cache[(ah, aw)]
+            aaf = a['s_L'][0]
+            for dh in range(max(ah - candidate_radius - 2, 0), min(ah + candidate_radius + 3, H)):
+                for dw in range(max(aw - candidate_radius - 2, 0), min(aw + candidate_radius + 3, W)):
+                    if (dh, dw) not in frame:
+                        continue
+                    d = frame[(dh, dw)]
+                    distance = euclidean(pos(aaf, a['spt']), pos(f, d['spt']))
+                    if distance < candidate_radius:
+                        pairs.append((aaf, ah, aw, dh, dw, distance))
+        pairs = sorted(pairs, key=lambda x: x[5])
+        for (aaf, ah, aw, dh, dw, distance) in pairs:
+            if (ah, aw) not in cache:
+                continue                                      # ancestor has been paired
+            elif frame[(dh, dw)]['a_L'] is not None:
+                continue                                      # descendant has been paired
+            frame[(dh, dw)]['a_L'] = (aaf, ah, aw)
+            assert bins[aaf][(ah, aw)]['d_L'] is None
+            bins[aaf][(ah, aw)]['d_L'] = (f, dh, dw)
+            del cache[(ah, aw)]
+    traces = []
+    for f in range(F):
+        for key in sorted(bins[f]):
+            b = bins[f][key]
+            if b['a_L'] is not None:
+                continue
+            trace = [None] * F
+            trace[f] = b['spt']
+            cur = b
+            while cur['d_L'] is not None:
+                df, dh, dw = cur['d_L']
+                cur = bins[df][(dh, dw)]
+                trace[df] = cur['spt']
+            traces.append(trace)
+    return traces, total_discarded

@@ -79,3 +79,55 @@ def test_tracking_batches_fields_and_timetrace_path():
     i, f = np.argwhere(live)[7]
     h, w = tt["track_hw"][i, f]
     assert tt["photometry"][i, f] == po.photometry_mexican_hat(m1[f].astype(np.int64), h, w)
+
+
+# ------------------------------------------------------------------------------------ greedy cross-frame tracking
+def _cycles(seed, F=6, H=96, W=96, n=120, p_off=0.25, jitter=1):
+    """spot lists of F frames of one field: a fixed population observed with +-jitter px noise and drop-outs,
+    plus a few spurious spots per frame; no two spots of a frame closer than 2 px (the reference's precondition)"""
+    rng = np.random.default_rng(seed)
+    base = np.stack([rng.integers(4, H - 4, n), rng.integers(4, W - 4, n)], axis=1)
+    frames = []
+    for f in range(F):
+        sel = rng.uniform(size=n) > p_off
+        pts = base[sel] + rng.integers(-jitter, jitter + 1, (int(sel.sum()), 2))
+        pts = np.concatenate([pts, np.stack([rng.integers(4, H - 4, 8), rng.integers(4, W - 4, 8)], axis=1)])
+        keep, seen = [], set()
+        for h, w in pts.tolist():
+            if all(abs(h - a) > 1 or abs(w - b) > 1 for a, b in seen):
+                seen.add((h, w)); keep.append((h, w))
+        frames.append(keep)
+    return frames
+
+
+def _traces_as_array(traces, F):
+    return np.array([[-1 if v is None else v for v in t] for t in traces], dtype=np.int64).reshape(-1, F)
+
+
+def test_greedy_tracking_matches_oracle():
+    """fsq_track_greedy against the oracle's restatement of Experiment.greedy_particle_tracking (parity unpinned:
+    restated by reading): identical traces in identical order -- ties in distance, skipped frames, drift offsets
+    with sub-pixel parts, drop-outs at the border, several fields per launch."""
+    from fluorosequencingimageanalysis_b200 import engine
+    shape = (96, 96)
+    offs = [(0, 0), (0.35, -1.6), (-0.35, 1.6), (2.0, 0.0), (-2.0, 0.5), (0.0, -0.5)]
+    fields = [_cycles(s) for s in (1, 2, 3)]
+    for radius in (2, 3):
+        for offsets in (None, offs):
+            got = engine.track_greedy_batch(fields, shape, candidate_radius=radius, offsets=offsets, spot_radius=0)
+            for fld, (tr, nd) in zip(fields, got):
+                want, wnd = tro.greedy_particle_tracking(fld, shape, candidate_radius=radius, offsets=offsets)
+                assert nd == wnd
+                assert np.array_equal(tr, _traces_as_array(want, 6)), (radius, offsets is None)
+            if offsets is None and radius == 2:
+                tr = got[0][0]
+                assert ((tr >= 0).sum(axis=1) >= 4).sum() > 30                 # long traces exist
+                gaps = [(t >= 0) for t in tr]
+                assert any(g[0] and not g[1] and g[2:].any() for g in gaps)    # ... and traces that skip a frame
+    one = engine.track_greedy_batch(fields[0], shape, spot_radius=3)
+    want, wnd = tro.greedy_particle_tracking(fields[0], shape, spot_radius=3)
+    assert one[1] == wnd and np.array_equal(one[0], _traces_as_array(want, 6))
+    with pytest.raises(ValueError):
+        engine.track_greedy_batch(fields[0], shape, offsets=[(1, 0)] * 6)       # flexlibrary.py:582-584
+    with pytest.raises(AssertionError):
+        engine.track_greedy_batch([[(10, 10), (10.2, 10.1)], [(10, 10)]], shape)   # :853-858

@@ -303,3 +303,28 @@ def test_track_oracle_known_answers():
         tro.make_spot((H, W), 10, 10, 4)
     with pytest.raises(AttributeError):
         tro.make_spot((H, W), 1, 10, 5)                     # the 5x5 square leaves the image
+
+
+def test_greedy_tracking_oracle_known_answers():
+    """Hand-checkable cases of the restated Experiment.greedy_particle_tracking (flexlibrary.py:680-1027)."""
+    from oracle import track_oracle as tro
+    shape = (40, 40)
+    # two ancestors compete for one candidate: the nearer one wins, the other one finds it again a frame later
+    f0 = [(10, 10), (10, 13)]
+    f1 = [(10, 11)]                      # distance 1 to (10,10), 2 to (10,13) -> not < 2: only the first is a pair
+    f2 = [(10, 12), (11, 13)]            # (10,11)->(10,12) d=1; the unpaired (10,13) of frame 0 -> (11,13) d=1, skipping frame 1
+    tr, nd = tro.greedy_particle_tracking([f0, f1, f2], shape)
+    assert nd == 0 and tr == [[0, 0, 0], [1, None, 1]]
+    # equal distances: the stable sort keeps ancestor raster order, so the ancestor that comes first in raster order gets the candidate
+    tr, _ = tro.greedy_particle_tracking([[(10, 10), (10, 12)], [(10, 11)]], shape)
+    assert tr == [[0, 0], [1, None]]
+    # drift: frame 1 is shifted by (+3, 0); with the offset the spots pair up, without it they do not
+    tr, _ = tro.greedy_particle_tracking([[(20, 20)], [(17, 20)]], shape, offsets=[(0, 0), (3, 0)])
+    assert tr == [[0, 0]]
+    tr, _ = tro.greedy_particle_tracking([[(20, 20)], [(17, 20)]], shape)
+    assert tr == [[0, None], [None, 0]]
+    # a spot that would leave the field in some frame of the sequence is dropped and counted (discard_dropouts)
+    tr, nd = tro.greedy_particle_tracking([[(1, 20), (20, 20)], [(20, 20)]], shape, offsets=[(0, 0), (3, 0)])
+    assert nd == 1 and tr == [[1, None], [None, 0]]
+    with pytest.raises(ValueError):
+        tro.accumulate_offsets([(1, 0), (0, 0)])
