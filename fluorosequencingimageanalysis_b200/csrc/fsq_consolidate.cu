@@ -206,6 +206,16 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
 }
 
 // one walk per accepted candidate; only the first member of a component completes it and replays pflib.py:479-512
+// one rival list = 16 shorts = two 16-byte loads
+struct AdjRow { short v[CONS_MAXDEG]; };
+__device__ __forceinline__ AdjRow cons_ld_adj(const short* adj, long long k) {
+    AdjRow r;
+    const int4* p = reinterpret_cast<const int4*>(adj + k * CONS_MAXDEG);
+    *reinterpret_cast<int4*>(&r.v[0]) = __ldg(p);
+    *reinterpret_cast<int4*>(&r.v[8]) = __ldg(p + 1);
+    return r;
+}
+
 __global__ void __launch_bounds__(128)
 cons_component_kernel(ConsScratch s) {
     const long long m = *s.m_total;
@@ -217,9 +227,11 @@ cons_component_kernel(ConsScratch s) {
     for (int i = 0; i < cnt; ++i) {
         const int k = member[i];
         const int dk = s.deg[k];
-        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
-        for (int r = 0; r < dk; ++r) {
-            const int j = k + adj[r];
+        const AdjRow row = cons_ld_adj(s.adj, k);
+#pragma unroll
+        for (int r = 0; r < CONS_MAXDEG; ++r) {
+            if (r >= dk) break;
+            const int j = k + row.v[r];
             if (j < (int)a) return;                            // an earlier member exists: it does the work
             bool seen = false;
             for (int t = 0; t < cnt; ++t) seen |= (member[t] == j);
@@ -229,6 +241,7 @@ cons_component_kernel(ConsScratch s) {
             }
         }
     }
+    if (cnt == 1) return;                                      // no rivals: stays alive
     // raster order = ascending position (insertion sort; the walk leaves the list nearly sorted)
     for (int i = 1; i < cnt; ++i) {
         const int v = member[i];
@@ -236,19 +249,28 @@ cons_component_kernel(ConsScratch s) {
         while (t >= 0 && member[t] > v) { member[t + 1] = member[t]; --t; }
         member[t + 1] = v;
     }
+    // the replay runs on a private copy: R^2 of every member (independent loads) and a 64-bit alive mask
+    double r2m[CONS_MAXCOMP];
+    for (int t = 0; t < cnt; ++t) r2m[t] = s.val[member[t]].r2;
+    unsigned long long alive = ~0ull;
     for (int i = 0; i < cnt; ++i) {
+        if (!((alive >> i) & 1ull)) continue;                  // "skip pixels that have had their psfs deleted" (:481)
         const int k = member[i];
-        if (!s.alive[k]) continue;                             // "skip pixels that have had their psfs deleted" (:481)
-        const double r2k = s.val[k].r2;
         const int dk = s.deg[k];
-        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
-        for (int r = 0; r < dk; ++r) {                         // itertools.product(h_range, w_range): raster order
-            const int j = k + adj[r];
-            if (!s.alive[j]) continue;
-            if (r2k > s.val[j].r2) s.alive[j] = 0;             // :508-509
-            else { s.alive[k] = 0; break; }                    // :510-512
+        const AdjRow row = cons_ld_adj(s.adj, k);
+#pragma unroll
+        for (int r = 0; r < CONS_MAXDEG; ++r) {                // itertools.product(h_range, w_range): raster order
+            if (r >= dk) break;
+            const int j = k + row.v[r];
+            int t = 0;
+            while (t < cnt - 1 && member[t] != j) ++t;         // (every rival is a member)
+            if (!((alive >> t) & 1ull)) continue;
+            if (r2m[i] > r2m[t]) alive &= ~(1ull << t);        // :508-509
+            else { alive &= ~(1ull << i); break; }             // :510-512
         }
     }
+    for (int t = 0; t < cnt; ++t)
+        if (!((alive >> t) & 1ull)) s.alive[member[t]] = 0;
 }
 
 // Exact fallback for frames whose rival graph exceeds the limits of the two kernels above (extremely dense or
@@ -299,7 +321,10 @@ cons_finish_kernel(ConsScratch s, int reach, unsigned char* __restrict__ psf_sta
     const bool moved = (kh != ha.h) || (kw != ha.w);
     psf_state[ha.idx] = moved ? 3 : 2;
     psf_key[2 * ha.idx] = kh; psf_key[2 * ha.idx + 1] = kw;
-    if (n_psf) atomicAdd(&n_psf[ha.f], 1ull);
+    if (n_psf) {                                               // one atomic per (warp, frame): candidates are sorted by frame
+        const unsigned peers = __match_any_sync(__activemask(), ha.f);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&n_psf[ha.f], (unsigned long long)__popc(peers));
+    }
     if (moved) {
         // :518 asserts that the new key is free at the moment of the move: earlier survivors sit at their FINAL
         // keys by then, later ones still at their candidate pixels.  (Cannot happen when the fitted centre lies
@@ -352,47 +377,50 @@ pack_count_kernel(const unsigned char* __restrict__ state, const int32_t* __rest
     const long long nt = cons_n(n, n_dev);
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     const int st = i < nt ? state[i] : 0;
-    if (st == 2) atomicAdd((unsigned long long*)&s.frameU[cand_frame[i]], 1ull);
-    if (st == 3) atomicAdd((unsigned long long*)&s.frameM[cand_frame[i]], 1ull);
+    if (st >= 2) {                                             // one atomic per (warp, frame, class)
+        const int key = cand_frame[i] * 2 + (st - 2);
+        const unsigned peers = __match_any_sync(__activemask(), key);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1))
+            atomicAdd((unsigned long long*)(st == 2 ? &s.frameU[cand_frame[i]] : &s.frameM[cand_frame[i]]), (unsigned long long)__popc(peers));
+    }
     const int cu = __syncthreads_count(st == 2);
     const int cm = __syncthreads_count(st == 3);
     if (threadIdx.x == 0) { s.blockU[blockIdx.x] = cu; s.blockM[blockIdx.x] = cm; }
 }
 
+// exclusive scans of two arrays at once (one block of 1024 threads; the two share every barrier)
 template <typename T>
-__device__ void block_exclusive_scan(T* v, long long count, long long* total_out) {     // one block of 1024 threads
-    __shared__ long long buf[1024];
-    __shared__ long long carry;
+__device__ void block_exclusive_scan2(T* u, T* v, long long count, long long* u_total, long long* v_total) {
+    __shared__ long long bu[1024], bv[1024];
+    __shared__ long long cu, cv;
     const int tid = threadIdx.x;
     __syncthreads();
-    if (tid == 0) carry = 0;
+    if (tid == 0) { cu = 0; cv = 0; }
     __syncthreads();
     for (long long base = 0; base < count; base += 1024) {
         const long long b = base + tid;
-        const long long x = b < count ? (long long)v[b] : 0;
-        buf[tid] = x;
+        const long long xu = b < count ? (long long)u[b] : 0, xv = b < count ? (long long)v[b] : 0;
+        bu[tid] = xu; bv[tid] = xv;
         __syncthreads();
         for (int d = 1; d < 1024; d <<= 1) {
-            const long long t = tid >= d ? buf[tid - d] : 0;
+            const long long tu = tid >= d ? bu[tid - d] : 0, tv = tid >= d ? bv[tid - d] : 0;
             __syncthreads();
-            buf[tid] += t;
+            bu[tid] += tu; bv[tid] += tv;
             __syncthreads();
         }
-        if (b < count) v[b] = (T)(carry + buf[tid] - x);
+        if (b < count) { u[b] = (T)(cu + bu[tid] - xu); v[b] = (T)(cv + bv[tid] - xv); }
         __syncthreads();
-        if (tid == 1023) carry += buf[1023];
+        if (tid == 1023) { cu += bu[1023]; cv += bv[1023]; }
         __syncthreads();
     }
-    if (tid == 0 && total_out) *total_out = carry;
+    if (tid == 0) { if (u_total) *u_total = cu; if (v_total) *v_total = cv; }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024)
 pack_scan_kernel(PackScratch s, long long nb, int F, long long* __restrict__ psf_base) {
-    block_exclusive_scan(s.blockU, nb, nullptr);
-    block_exclusive_scan(s.blockM, nb, nullptr);
-    block_exclusive_scan(s.frameU, F, &s.frameU[F]);
-    block_exclusive_scan(s.frameM, F, &s.frameM[F]);
+    block_exclusive_scan2(s.blockU, s.blockM, nb, nullptr, nullptr);
+    block_exclusive_scan2(s.frameU, s.frameM, F, &s.frameU[F], &s.frameM[F]);
     for (int f = threadIdx.x; f <= F; f += 1024) psf_base[f] = s.frameU[f] + s.frameM[f];
 }
 
