@@ -206,16 +206,8 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
 }
 
 // one walk per accepted candidate; only the first member of a component completes it and replays pflib.py:479-512
-// one rival list = 16 shorts = two 16-byte loads
-struct AdjRow { short v[CONS_MAXDEG]; };
-__device__ __forceinline__ AdjRow cons_ld_adj(const short* adj, long long k) {
-    AdjRow r;
-    const int4* p = reinterpret_cast<const int4*>(adj + k * CONS_MAXDEG);
-    *reinterpret_cast<int4*>(&r.v[0]) = __ldg(p);
-    *reinterpret_cast<int4*>(&r.v[8]) = __ldg(p + 1);
-    return r;
-}
-
+// (Loading a rival list as two 16-byte vectors and replaying on a private copy of the members' R^2 / alive bits was
+//  measured: 70 us instead of 58 us per 40-frame batch -- the local arrays cost more than the loads they save.)
 __global__ void __launch_bounds__(128)
 cons_component_kernel(ConsScratch s) {
     const long long m = *s.m_total;
@@ -227,11 +219,9 @@ cons_component_kernel(ConsScratch s) {
     for (int i = 0; i < cnt; ++i) {
         const int k = member[i];
         const int dk = s.deg[k];
-        const AdjRow row = cons_ld_adj(s.adj, k);
-#pragma unroll
-        for (int r = 0; r < CONS_MAXDEG; ++r) {
-            if (r >= dk) break;
-            const int j = k + row.v[r];
+        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
+        for (int r = 0; r < dk; ++r) {
+            const int j = k + adj[r];
             if (j < (int)a) return;                            // an earlier member exists: it does the work
             bool seen = false;
             for (int t = 0; t < cnt; ++t) seen |= (member[t] == j);
@@ -241,7 +231,6 @@ cons_component_kernel(ConsScratch s) {
             }
         }
     }
-    if (cnt == 1) return;                                      // no rivals: stays alive
     // raster order = ascending position (insertion sort; the walk leaves the list nearly sorted)
     for (int i = 1; i < cnt; ++i) {
         const int v = member[i];
@@ -249,28 +238,19 @@ cons_component_kernel(ConsScratch s) {
         while (t >= 0 && member[t] > v) { member[t + 1] = member[t]; --t; }
         member[t + 1] = v;
     }
-    // the replay runs on a private copy: R^2 of every member (independent loads) and a 64-bit alive mask
-    double r2m[CONS_MAXCOMP];
-    for (int t = 0; t < cnt; ++t) r2m[t] = s.val[member[t]].r2;
-    unsigned long long alive = ~0ull;
     for (int i = 0; i < cnt; ++i) {
-        if (!((alive >> i) & 1ull)) continue;                  // "skip pixels that have had their psfs deleted" (:481)
         const int k = member[i];
+        if (!s.alive[k]) continue;                             // "skip pixels that have had their psfs deleted" (:481)
+        const double r2k = s.val[k].r2;
         const int dk = s.deg[k];
-        const AdjRow row = cons_ld_adj(s.adj, k);
-#pragma unroll
-        for (int r = 0; r < CONS_MAXDEG; ++r) {                // itertools.product(h_range, w_range): raster order
-            if (r >= dk) break;
-            const int j = k + row.v[r];
-            int t = 0;
-            while (t < cnt - 1 && member[t] != j) ++t;         // (every rival is a member)
-            if (!((alive >> t) & 1ull)) continue;
-            if (r2m[i] > r2m[t]) alive &= ~(1ull << t);        // :508-509
-            else { alive &= ~(1ull << i); break; }             // :510-512
+        const short* adj = s.adj + (long long)k * CONS_MAXDEG;
+        for (int r = 0; r < dk; ++r) {                         // itertools.product(h_range, w_range): raster order
+            const int j = k + adj[r];
+            if (!s.alive[j]) continue;
+            if (r2k > s.val[j].r2) s.alive[j] = 0;             // :508-509
+            else { s.alive[k] = 0; break; }                    // :510-512
         }
     }
-    for (int t = 0; t < cnt; ++t)
-        if (!((alive >> t) & 1ull)) s.alive[member[t]] = 0;
 }
 
 // Exact fallback for frames whose rival graph exceeds the limits of the two kernels above (extremely dense or
