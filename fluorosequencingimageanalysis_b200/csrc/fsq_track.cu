@@ -63,10 +63,14 @@ track_greedy_kernel(const TrackArgs a) {
                 if (!(a.spot_radius <= gh && gh < (double)H - 0.5 - a.spot_radius &&
                       a.spot_radius <= gw && gw < (double)W - 0.5 - a.spot_radius)) { drop = true; break; }
             }
+            const int bh = (int)round(oh), bw = (int)round(ow);             // python-2 round(): half away from zero
+            // (with cumulative offsets that start at (0, 0) a kept spot always rounds into the frame; the guard only
+            //  protects the index grids against offsets that do not)
+            if (!drop && (bh < 0 || bh >= H || bw < 0 || bw >= W)) drop = true;
             a.pos[2 * i] = oh; a.pos[2 * i + 1] = ow;
             a.discarded[i] = drop ? 1 : 0;
-            a.bin_hw[2 * i] = drop ? -1 : (int)round(oh);                   // python-2 round(): half away from zero
-            a.bin_hw[2 * i + 1] = drop ? -1 : (int)round(ow);
+            a.bin_hw[2 * i] = drop ? -1 : bh;
+            a.bin_hw[2 * i + 1] = drop ? -1 : bw;
             a.anc[i] = -1; a.desc[i] = -1;
         }
     }
