@@ -258,14 +258,22 @@ def run_ours(args):
     L = _lib.load()
     solver, faithful = SOLVERS[args.solver]
     warmup = max(args.warmup, 3)
-    # ---- synthetic inputs: N_VARIANTS different 40-frame stacks, host (pinned) and device copies
+    # ---- steps per launch: G stacks (steps) go through the kernels together; G divides the number of timed steps
+    G = max(1, min(args.stacks_per_launch, args.steps))
+    while args.steps % G:
+        G -= 1
+    n_launch = args.steps // G                    # launches in each timed region: n_launch * G = args.steps steps exactly
+    w_launch = max(3, -(-warmup // G))
+    FL = N_FRAMES * G                             # frames per launch
+    # ---- synthetic inputs: N_VARIANTS different groups of G 40-frame stacks, host (pinned) and device copies
+    base_stacks = [make_stack(1 + 100 * rank + v) for v in range(N_VARIANTS)]
     stacks_host = []
     for v in range(N_VARIANTS):
-        st = make_stack(1 + 100 * rank + v)
+        st = np.concatenate([base_stacks[(v + j) % N_VARIANTS] for j in range(G)]) if G > 1 else base_stacks[v]
         t = torch.from_numpy(st.view(np.int16)).view(torch.uint16).pin_memory()
         stacks_host.append(t)
     stacks_dev = [t.to(dev) for t in stacks_host]
-    in_bytes = N_FRAMES * H * W * 2
+    in_bytes = FL * H * W * 2
     kw = dict(dtype=torch.uint16, faithful=faithful, solver=solver)
     if args.park is not None:
         kw["park_after"] = args.park
@@ -275,8 +283,8 @@ def run_ours(args):
     cur = torch.cuda.current_stream()
 
     # ---- timed region A: inputs resident in HBM; K steps software-pipelined over `depth` streams
-    fs = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=False, **kw)
-    totals = torch.zeros(max(args.steps, warmup), dtype=torch.int64, device=dev)
+    fs = engine.FieldStream(FL, H, W, depth=args.depth, host_io=False, **kw)
+    totals = torch.zeros(max(n_launch, w_launch), dtype=torch.int64, device=dev)
 
     def resident_steps(n_steps, first):
         for k in range(n_steps):
@@ -288,22 +296,22 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    resident_steps(warmup, 0)
+    resident_steps(w_launch, 0)
     torch.cuda.synchronize()
     n_probe = int(totals[0].item())
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     win_a0 = time.perf_counter()
     ev[0].record()
-    resident_steps(args.steps, 3)
+    resident_steps(n_launch, 3)
     ev[1].record()
     host_enqueue_ms = (time.perf_counter() - win_a0) * 1e3 / args.steps      # host time to queue one step
     barrier()
     win_a1 = time.perf_counter()
     ms_total = ev[0].elapsed_time(ev[1])
-    fits_total = int(totals[:args.steps].sum().item())
+    fits_total = int(totals[:n_launch].sum().item())
     pipe = fs.slots[0]["pipe"]
-    if int(totals[:args.steps].max().item()) > pipe.cap:
+    if int(totals[:n_launch].max().item()) > pipe.cap:
         raise RuntimeError("candidate capacity exceeded")
 
     # ---- fit launches alone (roofline): re-fit the last detection of slot 0, events per launch
@@ -342,7 +350,7 @@ def run_ours(args):
 
     # ---- timed region B (e2e): pinned host frames in, packed results back on the host, every step;
     #      submit(k) / begin_fetch(k-1) / end_fetch(k-2) keeps H2D, kernels and D2H of neighbouring steps in flight
-    fe = engine.FieldStream(N_FRAMES, H, W, depth=args.depth, host_io=True, fetch=args.fetch, **kw)
+    fe = engine.FieldStream(FL, H, W, depth=args.depth, host_io=True, fetch=args.fetch, **kw)
 
     def e2e_steps(n_steps, first):
         # submit(k), begin_fetch(k - depth + 2), end_fetch(k - depth + 1): depth - 1 batches stay in flight,
@@ -367,7 +375,7 @@ def run_ours(args):
     e2e_steps(max(3, args.depth), 0)
     barrier()
     t0 = time.perf_counter()
-    e2e_fits, d2h = e2e_steps(args.steps, 2)
+    e2e_fits, d2h = e2e_steps(n_launch, 2)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop([(win_a0, win_a1), (t0, t0 + e2e_s)])
@@ -376,11 +384,11 @@ def run_ours(args):
     parity = None
     if rank == 0 and solver != "minpack" and not args.no_parity_solver:
         pp = engine.FieldPipeline(N_FRAMES, H, W, dtype=torch.uint16, faithful=True, solver="minpack")
-        pp.run(frames_k)
+        pp.run(frames_k[:N_FRAMES])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pp.run(frames_k)
+        pp.run(frames_k[:N_FRAMES])
         e1.record()
         e1.synchronize()
         parity = {"solver": "minpack-faithful (reference behaviour incl. qrsolv diagonal view, FD Jacobian, QR)",
@@ -431,14 +439,17 @@ def run_ours(args):
         pass
     lm_traffic = traffic.get("lmwarp_kernel", {}).get("bytes") if solver == "fast" else None
     det_traffic = traffic.get("detect_cm_packed_kernel", {}).get("bytes")
-    det_bytes = N_FRAMES * H * W * 2 + 8 * n_last
+    if G > 1:                               # the ncu captures are of one-stack launches: G stacks move G times the bytes
+        lm_traffic = lm_traffic * G if lm_traffic else None
+        det_traffic = det_traffic * G if det_traffic else None
+    det_bytes = FL * H * W * 2 + 8 * n_last
     det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
     kname = {"fast": "lmwarp_kernel (+ fit_prep_kernel, fit_finish_kernel) behind fsq_fit_candidates",
              "fast64": "lmfast_kernel<double,true>", "minpack": "lmfit_kernel<8,true>"}[solver]
     roofline = {"bound": pk, "achieved": achieved, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (peak[pk] / 1e12), "traffic": lm_traffic,
-                "achieved_in_pipeline": flops / n_last * (fits_all / world / args.steps) / (ms_total / args.steps * 1e-3) / 1e12,
-                "frac_in_pipeline": flops / n_last * (fits_all / world / args.steps) / (ms_total / args.steps * 1e-3) / peak[pk],
+                "achieved_in_pipeline": flops / n_last * (fits_all / world) / (ms_total * 1e-3) / 1e12,
+                "frac_in_pipeline": flops / n_last * (fits_all / world) / (ms_total * 1e-3) / peak[pk],
                 "kernel": kname, "ms_per_launch": fit_ms_avg,
                 "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "passes_per_launch": sum_nfev,
                 "flop_per_lm_iteration": fl_iter,
@@ -470,20 +481,21 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32" if solver == "fast" else "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots (sigma 1.5), every frame: "
+        "config": {"workload": "configs[1]: 40-frame stack of one 512x512 field, ~500 spots (sigma 1.5) = one step; "
+                               + ("%d stacks go through the kernels per launch; " % G if G > 1 else "") + "every frame: "
                                "detection + 5x5 LM fit of every candidate + metrics",
-                   "frames_per_step": N_FRAMES, "candidates_per_step": n_probe,
+                   "frames_per_step": N_FRAMES, "candidates_per_step": n_probe // G, "stacks_per_launch": G,
                    "solver": args.solver, "pipeline_depth": args.depth, "lm_warps_per_sm_per_batch": args.warps_per_sm,
                    "l2": "8 different stacks cycled (168 MB > 126 MB L2): inputs larger than L2", "parallelism": "field-sharded x%d, no collective" % world},
-        "frames_per_s": frames_per_s, "serial_ms_per_step": serial_ms_per_step,
+        "frames_per_s": frames_per_s, "serial_ms_per_step": serial_ms_per_step / G,
         "host_enqueue_ms_per_step": host_enqueue_ms,
-        "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes,
+        "e2e": {"value": e2e_fits_all / (e2e_ms * 1e-3), "unit": "fits/s", "h2d_bytes_per_step": in_bytes // G,
                 "d2h_bytes_per_step": d2h // max(args.steps, 1), "frames_per_s": world * args.steps * N_FRAMES / (e2e_ms * 1e-3),
                 "returns": ("final PSF records of find_peptides (R^2 gate, consolidation, re-key on the device)" if args.fetch == "psfs"
                             else "every candidate's fit record"),
                 "api": "engine.FieldStream submit/begin_fetch/end_fetch over fsq_detect / fsq_fit_candidates"
                        + (" / fsq_consolidate / fsq_pack_psfs" if args.fetch == "psfs" else "") + " (pinned host frames in, packed results out)"},
-        "gpu_launches": args.steps * fs.kernels_per_run,
+        "gpu_launches": n_launch * fs.kernels_per_run,
         "clocks": clocks, "roofline": roofline, "roofline_detect": roofline_detect,
     }
     if parity is not None:
@@ -503,12 +515,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--solver", default="fast", choices=["fast", "fast64", "minpack-faithful", "minpack-clean"])
-    ap.add_argument("--depth", type=int, default=6, help="batches in flight (streams) in the pipelined regions")
+    ap.add_argument("--depth", type=int, default=5, help="launches in flight (streams) in the pipelined regions")
     ap.add_argument("--no-parity-solver", action="store_true")
     ap.add_argument("--park", type=int, default=None, help="fsq_lm_opts.park_after override (scheduling only)")
     ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
                     help="fsq_lm_opts.warps_per_sm: warps per SM of ONE batch's LM launch (scheduling only; 0 = fill the SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stacks-per-launch", type=int, default=4,
+                    help="40-frame stacks (steps) processed by one pass of the kernels: a larger launch amortises the "
+                         "drain of each LM launch's last long fits; reduced to a divisor of --steps")
     ap.add_argument("--fetch", default="psfs", choices=["psfs", "candidates"],
                     help="what a step returns to the host in the e2e region: the final PSF records of find_peptides "
                          "(R^2 gate + consolidation + re-key on the device; default) or every candidate's fit record")
