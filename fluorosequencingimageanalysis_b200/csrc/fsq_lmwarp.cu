@@ -66,6 +66,7 @@ struct WarpArgs {
     struct StragRec* strag;                  // parked fit states
     struct PrepRec* prep;                    // per-candidate start records
     int cap;                                 // phase 1: park a fit after this many passes (0 = never)
+    int drain_grace;                         // phase 1: once the queue is empty, park what is still running after this many ticks (0 = never)
     int resume;                              // phase 2: the work list is strag[0 .. *strag_count)
 };
 
@@ -418,9 +419,11 @@ lmwarp_kernel(const WarpArgs a) {
     //  candidates per atomic, records prefetched, claims shrinking to 1 towards the end of the queue) avoids that
     //  imbalance and measured no gain either (1.86 vs 1.78 ms; 160 frames and the pipelined step unchanged): the
     //  refill's round trips are hidden by the other resident warps.  The queue stays strictly on demand.)
+    int drained_ticks = 0;                              // warp-uniform: ticks since this warp first found the queue empty
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
         __syncwarp();
+        if (a.drain_grace > 0 && __any_sync(0xffffffffu, exhausted)) ++drained_ticks;
         const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
         if (want) {
             const int leader = __ffs(want) - 1;
@@ -552,7 +555,8 @@ lmwarp_kernel(const WarpArgs a) {
                 }
                 if (status == 0 && !accepted && (nonfinite || !isfinite(ratio))) status = -16;   // :1330-1335
                 have_new = accepted;
-                if (status == 0 && accepted && a.cap > 0 && nfev >= a.cap) {
+                if (status == 0 && accepted &&
+                    ((a.cap > 0 && nfev >= a.cap) || (a.drain_grace > 0 && drained_ticks > a.drain_grace))) {
                     // ------------------------------------------------------ park: a long fit leaves the lane
                     StragRec* rec = a.strag + atomicAdd(a.strag_count, 1ull);
                     rec->idx = idx;
@@ -853,16 +857,21 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
     long long blocks = (long long)sm_count() * use_per_sm;
     const long long need = (a.n + TPB - 1) / TPB;
     if (need < blocks) blocks = need < 1 ? 1 : need;
-    const int park = a.o.park_after > 0 ? a.o.park_after : 0;
-    a.cap = park; a.resume = 0;
+    // park_after > 0: park every fit after that many passes; park_after < 0: drain parking -- once the queue is
+    // empty, the fits still running -park_after ticks later (the 100+-iteration stragglers) are parked, so that the
+    // launch gives its SM slots back instead of keeping hundreds of warps alive for one lane each; the second launch
+    // finishes them packed into a few blocks
+    const int park = a.o.park_after;
+    a.cap = park > 0 ? park : 0; a.drain_grace = park < 0 ? -park : 0; a.resume = 0;
     lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks, TPB, smem, st>>>(a);
     FSQ_LAUNCH_CHECK();
-    if (park > 0) {
+    if (park != 0) {
         FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
-        a.cap = 0; a.resume = 1;
+        a.cap = 0; a.drain_grace = 0; a.resume = 1;
         // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
         // whatever the caller has queued on other streams (the next batch's detection and phase 1)
-        const long long blocks2 = blocks < sm_count() ? blocks : sm_count();
+        const long long want2 = park < 0 ? 16 : sm_count();
+        const long long blocks2 = blocks < want2 ? blocks : want2;
         lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks2, TPB, smem, st>>>(a);
         FSQ_LAUNCH_CHECK();
     }
@@ -920,7 +929,7 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     // when parking is requested, the parked states
     fsq_lm_opts o = *opts;
     void* scratch = nullptr;
-    const size_t bytes = (size_t)(o.park_after > 0 ? 64 + sizeof(StragRec) * (size_t)n : 64);
+    const size_t bytes = (size_t)(o.park_after != 0 ? 64 + sizeof(StragRec) * (size_t)n : 64);
     FSQ_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
     unsigned long long* head = (unsigned long long*)scratch;
     a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);

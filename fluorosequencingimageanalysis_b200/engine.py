@@ -667,6 +667,8 @@ class FieldPipeline(object):
         self.K = _check_kernel(correlation_matrix)
         self.mf = int(median_filter_size)
         self.c_std = float(c_std)
+        if park_after is None and solver == "fast":
+            park_after = -8        # drain parking (fsq.h): stragglers leave the launch once the queue is empty; scheduling only
         self.opts = _lib.default_opts(faithful=faithful, solver=solver, park_after=park_after, warps_per_sm=warps_per_sm)
         self.solver = solver
         if cap_per_frame is None:
@@ -684,7 +686,7 @@ class FieldPipeline(object):
         self.fit_sbytes = self.L.fsq_fit_scratch_bytes(self.cap)
         self.fit_scratch = torch.empty(self.fit_sbytes, dtype=torch.uint8, device=d)
         # cm, thr, rowmask, rowscan, framescan, emit + fit launches (FAST: prep, phase 1, phase 2 when parking, finish)
-        self.kernels_per_run = 6 + ((3 + (1 if self.opts.park_after > 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
+        self.kernels_per_run = 6 + ((3 + (1 if self.opts.park_after != 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
         # optional tail of find_peptides on the device: R^2 gate + consolidation + re-key (7 launches), packed
         # final PSFs in dictionary order (3 launches) -- what then leaves the device is ~1 record per spot
         self.consolidate = bool(consolidate)

@@ -96,11 +96,16 @@ typedef struct fsq_lm_opts {
                               (mpfit.py:1915,1956,1976-1977); 0: clean MINPACK            */
     int32_t want_perror;/* 1: compute covariance -> perror (mpfit.py:1361-1388); MINPACK solver only */
     int32_t solver;     /* FSQ_SOLVER_*                                                    */
-    int32_t park_after; /* FAST solver scheduling only (results do not depend on it): a fit that
-                           has not ended after this many passes over its window is parked and
-                           finished by a second launch over the parked fits, so that a handful of
-                           100+-iteration fits do not pin whole thread blocks.  0 = one launch
-                           (default; on B200 the two-launch schedule measured no faster).   */
+    int32_t park_after; /* FAST solver scheduling only (results do not depend on it).
+                           > 0: a fit that has not ended after this many passes over its window is parked and
+                                finished by a second launch over the parked fits;
+                           < 0: drain parking -- once the work queue is empty, whatever is still running
+                                -park_after iterations later (the 100+-iteration stragglers, 0.1 % of the fits)
+                                is parked, so the launch returns its SM slots instead of keeping hundreds of
+                                warps alive for one lane each; a second launch finishes the parked fits packed
+                                into 16 blocks.  Measured on B200 in the pipelined step: +4 % (four stacks per
+                                launch) to +16 % (one stack per launch); engine.FieldPipeline uses -8.
+                           0 = one launch (default).                                          */
     int32_t warps_per_sm;/* FAST solver scheduling only: warps per SM of the persistent LM launch: 8 (= 0,
                            the default: the launch fills the machine), 4, 2 or 1.  A small value leaves
                            most of every SM to launches queued on other streams: with several batches in

@@ -100,7 +100,7 @@ def test_fast_scheduling_never_changes_a_result(frame0):
     frd = engine.to_device_frames(stack)
     det = engine.detect_batch(frd)
     base = None
-    for park, wps in ((0, 0), (8, 0), (32, 0), (0, 4), (0, 2), (0, 1), (16, 2)):
+    for park, wps in ((0, 0), (8, 0), (32, 0), (0, 4), (0, 2), (0, 1), (16, 2), (-4, 0), (-24, 4)):   # negative: drain parking
         o = _lib.default_opts(faithful=False, solver="fast", park_after=park, warps_per_sm=wps)
         fit, ints, _ = engine.fit_candidates(frd, det.cand_hw, det.cand_frame, det.total, opts=o)
         fit, ints = fit.cpu().numpy(), ints.cpu().numpy()
