@@ -9,6 +9,7 @@ transliteration of the three reference files that hold the hot path
     /root/reference/agpy/gaussfitter.py      (lines 1-255: moments/twodgaussian/gaussfit)
     /root/reference/pflib.py                 (_psf_candidates, _fit_2d_gaussian, find_peptides ...)
     /root/reference/phase_correlate.py       (frame registration; one numpy-2 API rewrite)
+    /root/reference/flexlibrary.py           (lines 1-1319: Spot / Image / Experiment -- photometry, the two trackers)
 
 The reference is Python 2 and does not parse under the Python 3.12 of this
 image.  This script plays the role a
@@ -133,8 +134,52 @@ def convert_phase_correlate(src):
               .replace("np.array(reg_image, dtype=np.float64, copy=False)", "np.asarray(reg_image, dtype=np.float64)")
 
 
+_FLEX_HEADER = '''\
+# ---- prologue injected by oracle/build_ref.py (py2 semantics shims, absent third-party modules) ----
+import math as _math
+def round(x, _floor=_math.floor):
+    """Python-2 round(): half away from zero (flexlibrary.py:605, 1233-1234 rely on it)."""
+    x = float(x)
+    return _floor(x + 0.5) if x >= 0 else -_floor(-x + 0.5)
+# ---- end prologue ----
+'''
+
+
+def convert_flexlibrary(src):
+    """flexlibrary.py:1-1319 -- Spot, Image, Experiment (offset helpers, discard_dropouts, greedy_particle_tracking,
+    next_frame_spot_by_luminosity_centroid, luminosity_centroid_particle_tracking).  The classes below line 1320 are
+    consumers of the path (traces, step fitting, plotting), hold Python-2-only syntax (:1843) and are not needed by
+    any parity test.  Rewrites: imports of absent / renamed modules; `(size - 1) / 2`, which is an INTEGER division
+    in Python 2 (the value is used as a slice bound); numpy.object (removed from numpy); dict.iteritems."""
+    lines = src.splitlines(True)[:1319]
+    out = []
+    for s in lines:
+        if s.startswith("sys.path.insert(0, '/home/proteanseq/pflib')"):
+            s = "sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.abspath(__file__)))\n"
+        elif s.startswith("from scipy.misc import imread"):
+            s = "imread = None  # scipy.misc.imread removed from scipy; file I/O is off the path\n"
+        elif s.startswith("import cPickle"):
+            s = "import pickle as cPickle\n"
+        elif s.startswith("from scipy.ndimage.measurements import center_of_mass"):
+            s = "from scipy.ndimage import center_of_mass\n"
+        elif s.startswith("import photutils"):
+            s = "photutils = None  # absent; only the sextractor photometry uses it\n"
+        elif s.startswith("import stepfitting_library"):
+            s = "stepfitting_library = None  # Python-2 module; only the Trace classes below line 1320 use it\n"
+        s = s.replace("(size - 1) / 2", "(size - 1) // 2").replace("(self.size - 1) / 2", "(self.size - 1) // 2")
+        s = s.replace("dtype=np.object)", "dtype=object)")
+        s = s.replace(".iteritems()", ".items()")
+        out.append(s)
+    text = "".join(out)
+    marker = "import stepfitting_library"
+    idx = text.find("stepfitting_library = None")
+    idx = text.find("\n", idx) + 1
+    return text[:idx] + "\n" + _FLEX_HEADER + text[idx:]
+
+
 def build(ref_root="/root/reference", check=False, quiet=False):
     paths = {
+        "flexlibrary": os.path.join(ref_root, "flexlibrary.py"),
         "phase_correlate": os.path.join(ref_root, "phase_correlate.py"),
         "mpfit": os.path.join(ref_root, "agpy", "mpfit", "mpfit.py"),
         "gaussfitter": os.path.join(ref_root, "agpy", "gaussfitter.py"),
@@ -149,6 +194,7 @@ def build(ref_root="/root/reference", check=False, quiet=False):
         "gaussfitter": convert_gaussfitter(srcs["gaussfitter"]),
         "pflib": convert_pflib(srcs["pflib"]),
         "phase_correlate": convert_phase_correlate(srcs["phase_correlate"]),
+        "flexlibrary": convert_flexlibrary(srcs["flexlibrary"]),
     }
     if check:
         for k in conv:
@@ -170,8 +216,10 @@ def build(ref_root="/root/reference", check=False, quiet=False):
         f.write(conv["pflib"])
     with open(os.path.join(OUT, "phase_correlate.py"), "w") as f:
         f.write(conv["phase_correlate"])
+    with open(os.path.join(OUT, "flexlibrary_head.py"), "w") as f:
+        f.write(conv["flexlibrary"])
     # compile check: every output must parse
-    for rel in ("agpy/mpfit/mpfit.py", "gaussfitter.py", "pflib.py", "phase_correlate.py"):
+    for rel in ("agpy/mpfit/mpfit.py", "gaussfitter.py", "pflib.py", "phase_correlate.py", "flexlibrary_head.py"):
         p = os.path.join(OUT, rel)
         compile(open(p).read(), p, "exec")
     if not quiet:
@@ -196,6 +244,32 @@ def load():
         return p, g, m
     finally:
         # do not leave top-level names 'pflib'/'gaussfitter' pointing at the reference
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+        if OUT in sys.path:
+            sys.path.remove(OUT)
+
+
+def load_flexlibrary():
+    """The head of the reference's flexlibrary (Spot, Image, Experiment: flexlibrary.py:1-1319) from oracle/_ref, or
+    None.  It imports the reference's own pflib / phase_correlate from the same directory."""
+    path = os.path.join(OUT, "flexlibrary_head.py")
+    if not os.path.isfile(path):
+        return None
+    import importlib.util
+    saved = {k: sys.modules.get(k) for k in ("pflib", "gaussfitter", "agpy", "agpy.mpfit", "phase_correlate")}
+    sys.path.insert(0, OUT)
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        spec = importlib.util.spec_from_file_location("_ref_flexlibrary_head", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v

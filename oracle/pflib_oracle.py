@@ -17,8 +17,9 @@ The detection oracle is the closed form of SURVEY.md App. A written with numpy o
 scipy), so it is independent of the scipy routines the reference calls; the pin test checks
 it against the reference itself (oracle/_ref) and against KAT-2.
 
-Parity pin: see oracle/lm_oracle.py header.  Photometry has no runnable reference here
-(flexlibrary needs photutils): "parity unpinned" for photometry_* -- restated by reading.
+Parity pin: see oracle/lm_oracle.py header.
+photometry_* are pinned against the reference's own Spot.photometry (oracle/_ref/flexlibrary_head.py, built from
+flexlibrary.py:1-1319) by tests/test_oracle_pins.py.
 """
 import math
 

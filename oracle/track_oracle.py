@@ -5,8 +5,11 @@ Experiment.luminosity_centroid_particle_tracking), Spot.__init__ (flexlibrary.py
 (:123-147), Experiment.unapply_offset (:614-617) and pflib.illumina_s_n (pflib.py:261-281), with
 scipy.ndimage.center_of_mass as the reference imports it (:61).
 
-PARITY UNPINNED: flexlibrary is Python 2 and imports photutils / skimage (absent here), so this file was restated
-by reading, not validated against a run of the reference.  Only tests/ may import it.
+PINNED: the head of the reference's flexlibrary (lines 1-1319: Spot, Image, Experiment) is built into
+oracle/_ref/flexlibrary_head.py by oracle/build_ref.py (import stubs for absent modules, `(size - 1) / 2` as the
+integer division it is in Python 2) and tests/test_oracle_pins.py checks `track` and `greedy_particle_tracking` below
+against the reference's own Experiment.luminosity_centroid_particle_tracking / greedy_particle_tracking on seeded
+movies and spot lists (identical positions, traces, trace order, drop-out counts).  Only tests/ may import it.
 """
 import math
 

@@ -1,5 +1,6 @@
 """GPU parity: fsq_track_centroid (Experiment.luminosity_centroid_particle_tracking, flexlibrary.py:1173-1317)
-against the oracle's restatement (oracle/track_oracle.py -- restated by reading: flexlibrary cannot run here).
+against the oracle's restatement (oracle/track_oracle.py, pinned to the reference's own functions by
+tests/test_oracle_pins.py).
 Positions and states exact; the Illumina S/N bit for bit (integer sums, numpy's summation order for the std)."""
 import numpy as np
 import pytest
@@ -105,8 +106,8 @@ def _traces_as_array(traces, F):
 
 
 def test_greedy_tracking_matches_oracle():
-    """fsq_track_greedy against the oracle's restatement of Experiment.greedy_particle_tracking (parity unpinned:
-    restated by reading): identical traces in identical order -- ties in distance, skipped frames, drift offsets
+    """fsq_track_greedy against the oracle's restatement of Experiment.greedy_particle_tracking (pinned to the
+    reference's own function by tests/test_oracle_pins.py): identical traces in identical order -- ties in distance, skipped frames, drift offsets
     with sub-pixel parts, drop-outs at the border, several fields per launch."""
     from fluorosequencingimageanalysis_b200 import engine
     shape = (96, 96)

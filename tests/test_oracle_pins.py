@@ -148,3 +148,100 @@ def test_phase_correlate_golden_is_the_reference_output():
         assert [float(np.real(v)) for v in m.phase_correlate(a, b, 20)] == g["out20"][k].tolist()
     # sub-pixel drifts come back at the 1/20 px resolution the caller asks for (flexlibrary.py:1717)
     assert g["out20"][2][:2].tolist() == [-0.35, 1.6] and g["out20"][4][:2].tolist() == [-0.45, -0.15]
+
+
+# ------------------------------------------------------------------ flexlibrary: photometry and the two trackers
+def _flex():
+    from oracle import build_ref
+    fl = build_ref.load_flexlibrary()
+    if fl is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    return fl
+
+
+def test_photometry_oracle_equals_reference_spot_methods():
+    """oracle photometry_* == the reference's own Spot.photometry (flexlibrary.py:160-317, run from oracle/_ref),
+    interior spots and spots whose radius-9 / radius-5 slices are cut by the border."""
+    fl = _flex()
+    from fluorosequencingimageanalysis_b200 import synth
+    # int64 pixels: under the numpy of the reference's time Python's sum() over uint16 scalars ran in int64 (0 + uint16
+    # -> int64); numpy 2 keeps uint16 and wraps, which is not the reference's behaviour
+    img = synth.synth_frame(3, H=64, W=72, n_spots=25).astype(np.int64)
+    im = fl.Image(image=img)
+    rng = np.random.default_rng(1)
+    pts = [(2, 2), (61, 69), (2, 40), (30, 2), (61, 5), (9, 9), (40, 40)] + \
+          [(int(h), int(w)) for h, w in zip(rng.integers(2, 62, 40), rng.integers(2, 70, 40))]
+    for h, w in pts:
+        sp = fl.Spot(im, h, w, 5)
+        assert sp.photometry(method='mexican_hat') == po.photometry_mexican_hat(img.astype(np.int64), h, w)
+        assert sp.photometry(method='mexican_hat', radius=5, brim_size=2) == \
+            po.photometry_mexican_hat(img.astype(np.int64), h, w, brim_size=2, radius=5)
+        assert sp.photometry(method='simple') == po.photometry_simple(img, h, w)
+        assert sp.photometry(method='maximum') == po.photometry_maximum(img, h, w)
+        assert sp.illumina_s_n() == po.illumina_s_n(img[h - 2:h + 3, w - 2:w + 3])
+    with pytest.raises(AttributeError):
+        fl.Spot(im, 1, 10, 5)                                   # the 5x5 square leaves the image (flexlibrary.py:100-118)
+
+
+def _bleaching_movie(seed, F=8, H=72, W=64, n_spots=25):
+    from fluorosequencingimageanalysis_b200 import synth
+    rng, cr, cc, amp = synth.spot_layout(seed, H, W, n_spots)
+    off_at = rng.integers(2, F, n_spots)
+    out = np.empty((F, H, W), dtype=np.uint16)
+    for f in range(F):
+        on = off_at > f
+        out[f] = synth.add_noise(synth.render_clean(cr[on], cc[on], amp[on], H, W, 1.5, 400.0), np.random.default_rng(900 + 17 * seed + f))
+    return out, [(int(round(a)), int(round(b))) for a, b in zip(cr, cc)]
+
+
+def test_centroid_tracking_oracle_equals_reference():
+    """oracle track() == Experiment.luminosity_centroid_particle_tracking of the reference itself
+    (flexlibrary.py:1173-1317): bleaching spots, border spots, integer drift offsets."""
+    fl = _flex()
+    from oracle import track_oracle as tro
+    for seed in (1, 2):
+        mv, spots = _bleaching_movie(seed)
+        F, H, W = mv.shape
+        spots = spots + [(2, 2), (3, 3), (H - 3, W - 3), (4, 30), (40, W - 3), (6, 6), (50, 50)]
+        frames = [fl.Image(image=mv[f]) for f in range(F)]
+        for offsets in (None, [(f % 3 - 1, (f // 2) % 3 - 1) for f in range(F)]):
+            for radius, cutoff in ((3, 3.0), (2, 5.0)):
+                init = [fl.Spot(frames[0], h, w, 5) for h, w in spots]
+                ref = fl.Experiment.luminosity_centroid_particle_tracking(frames, init, search_radius=radius,
+                                                                          s_n_cutoff=cutoff, offsets=offsets)
+                hw, st, _ = tro.track(mv, spots, size=5, search_radius=radius, s_n_cutoff=cutoff, offsets=offsets)
+                for i, trace in enumerate(ref):
+                    got = [(-1, -1) if s is None else (s.h, s.w) for s in trace]
+                    assert got == [tuple(v) for v in hw[i].tolist()], (seed, radius, i)
+                if radius == 3:
+                    assert (st == 2).any() and (st == 0).any() and (st == 1).any()      # every branch is exercised
+
+
+def test_greedy_tracking_oracle_equals_reference():
+    """oracle greedy_particle_tracking == Experiment.greedy_particle_tracking of the reference itself
+    (flexlibrary.py:680-1027): same traces in the same order, same drop-out count -- ties in distance, skipped frames,
+    sub-pixel drift offsets.  (The reference cannot run with offsets=None: `for f in len(frame_spots)`, :787.)"""
+    fl = _flex()
+    from oracle import track_oracle as tro
+    shape = (48, 56)
+    rng = np.random.default_rng(4)
+    base = np.stack([rng.integers(4, 44, 45), rng.integers(4, 52, 45)], axis=1)
+    frames = []
+    for f in range(5):
+        sel = rng.uniform(size=len(base)) > 0.25
+        pts = np.concatenate([base[sel] + rng.integers(-1, 2, (int(sel.sum()), 2)), np.stack([rng.integers(4, 44, 4), rng.integers(4, 52, 4)], axis=1)])
+        keep = []
+        for h, w in pts.tolist():
+            if all(abs(h - a) > 1 or abs(w - b) > 1 for a, b in keep):
+                keep.append((h, w))
+        frames.append(keep)
+    dummy = fl.Image(image=np.zeros(shape, dtype=np.uint16))
+    for radius in (2, 3):
+        for offsets in ([(0, 0)] * 5, [(0, 0), (0.35, -1.6), (-0.35, 1.6), (2.0, 0.0), (-2.0, 0.5)]):
+            spots = [[fl.Spot(dummy, h, w, 5) for h, w in fr] for fr in frames]
+            ref, nd = fl.Experiment.greedy_particle_tracking(spots, shape, candidate_radius=radius, offsets=offsets, spot_radius=0)
+            want, wnd = tro.greedy_particle_tracking(frames, shape, candidate_radius=radius, offsets=offsets, spot_radius=0)
+            assert nd == wnd
+            as_idx = [[None if s is None else spots[f].index(s) for f, s in enumerate(tr)] for tr in ref]
+            assert as_idx == want, (radius, offsets[1])
+    assert any(t[0] is not None and t[1] is None and any(v is not None for v in t[2:]) for t in want)      # a trace that skips a frame
