@@ -279,7 +279,7 @@ def test_read_image_png_and_conversion(tmp_path):
         pflib.read_image(str(tmp_path / "missing.tif"))
 
 
-# ------------------------------------------------------------------ tracking oracle (restated by reading)
+# ------------------------------------------------------------------ tracking oracle: hand-checkable cases
 def test_track_oracle_known_answers():
     """Hand-checkable cases of the luminosity-centroid tracker's restatement (flexlibrary.py:1173-1317): the
     centroid follows a bright pixel, python-2 rounding at .5, None at the border, fall-back below the S/N cut-off."""
