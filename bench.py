@@ -446,19 +446,24 @@ def run_ours(args):
     det_gbs = det_bytes / (det_ms_avg * 1e-3) / 1e9
     kname = {"fast": "lmwarp_kernel (+ fit_prep_kernel, fit_finish_kernel) behind fsq_fit_candidates",
              "fast64": "lmfast_kernel<double,true>", "minpack": "lmfit_kernel<8,true>"}[solver]
-    roofline = {"bound": pk, "achieved": achieved, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (peak[pk] / 1e12), "traffic": lm_traffic,
-                "achieved_in_pipeline": flops / n_last * (fits_all / world) / (ms_total * 1e-3) / 1e12,
-                "frac_in_pipeline": flops / n_last * (fits_all / world) / (ms_total * 1e-3) / peak[pk],
+    pipe_tflops = flops / n_last * (fits_all / world) / (ms_total * 1e-3) / 1e12
+    roofline = {"bound": pk, "achieved": pipe_tflops, "peak": peak[pk] / 1e12, "unit": "TFLOP/s",
+                "frac": pipe_tflops / (peak[pk] / 1e12), "traffic": lm_traffic,
+                "achieved_lone_launch": achieved, "frac_lone_launch": achieved / (peak[pk] / 1e12),
+                "achieved_in_pipeline": pipe_tflops, "frac_in_pipeline": pipe_tflops / (peak[pk] / 1e12),
                 "kernel": kname, "ms_per_launch": fit_ms_avg,
                 "fits_per_launch": n_last, "lm_iterations_per_launch": sum_niter, "passes_per_launch": sum_nfev,
                 "flop_per_lm_iteration": fl_iter,
                 "peak_source": "fsq_fma_peak %s FMA micro-benchmark, measured in this run (of measured)" % pk.upper(),
                 "fp32_fma_peak_tflops": peak["fp32"] / 1e12, "fp64_fma_peak_tflops": peak["fp64"] / 1e12,
                 "share_of_serial_step": fit_ms_avg / serial_ms_per_step,
-                "note": "FLOPs by the SURVEY 8(d) convention; achieved = fit launches of one batch timed alone (CUDA events), "
-                        "achieved_in_pipeline = the same FLOPs over the whole pipelined step; the kernel keeps residual/chi^2 in "
-                        "FP64 and the Jacobian / normal equations / Cholesky in FP32, so the FP32 peak is an upper bound it cannot reach"}
+                "note": "FLOPs by the SURVEY 8(d) convention (3600 per executed LM iteration, from the device niter counters). "
+                        "achieved / frac = those FLOPs over the timed region A (CUDA events around all K steps), in which "
+                        "several LM launches share the GPU with each other and with the detection / consolidation kernels, so "
+                        "it is the kernel's sustained rate and a lower bound; *_lone_launch = one launch's fit kernels timed "
+                        "alone by CUDA events (one 4-warp block per SM, as launched in the pipeline: latency-bound on its own). "
+                        "The kernel keeps residual / chi^2 in FP64 and the Jacobian / normal equations / Cholesky in FP32, so "
+                        "the FP32 peak is an upper bound it cannot reach"}
     roofline_detect = {"bound": "hbm", "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": det_gbs / hbm_peak, "traffic": det_traffic, "peak_source": hbm_src,
                        "kernels": "detect_cm + thr + rowmask + scans + emit", "ms_per_launch": det_ms_avg,
