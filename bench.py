@@ -259,9 +259,12 @@ def run_ours(args):
     solver, faithful = SOLVERS[args.solver]
     warmup = max(args.warmup, 3)
     # ---- steps per launch: G stacks (steps) go through the kernels together; G divides the number of timed steps
-    G = max(1, min(args.stacks_per_launch, args.steps))
-    while args.steps % G:
-        G -= 1
+    if args.stacks_per_launch is None:            # automatic: 4 stacks per launch, else the nearest size that divides K
+        G = next(g for g in (4, 5, 6, 8, 7, 3, 2, 1) if args.steps % g == 0)
+    else:
+        G = max(1, min(args.stacks_per_launch, args.steps))
+        while args.steps % G:
+            G -= 1
     n_launch = args.steps // G                    # launches in each timed region: n_launch * G = args.steps steps exactly
     w_launch = max(3, -(-warmup // G))
     FL = N_FRAMES * G                             # frames per launch
@@ -526,9 +529,10 @@ def main():
     ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
                     help="fsq_lm_opts.warps_per_sm: warps per SM of ONE batch's LM launch (scheduling only; 0 = fill the SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stacks-per-launch", type=int, default=4,
+    ap.add_argument("--stacks-per-launch", type=int, default=None,
                     help="40-frame stacks (steps) processed by one pass of the kernels: a larger launch amortises the "
-                         "drain of each LM launch's last long fits; reduced to a divisor of --steps")
+                         "drain of each LM launch's last long fits; default: 4, or the nearest size that divides --steps; "
+                         "an explicit value is reduced to a divisor of --steps")
     ap.add_argument("--fetch", default="psfs", choices=["psfs", "candidates"],
                     help="what a step returns to the host in the e2e region: the final PSF records of find_peptides "
                          "(R^2 gate + consolidation + re-key on the device; default) or every candidate's fit record")
