@@ -467,11 +467,20 @@ def run_ours(args):
                         "alone by CUDA events (one 4-warp block per SM, as launched in the pipeline: latency-bound on its own). "
                         "The kernel keeps residual / chi^2 in FP64 and the Jacobian / normal equations / Cholesky in FP32, so "
                         "the FP32 peak is an upper bound it cannot reach"}
-    roofline_detect = {"bound": "hbm", "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
+    alu_pct, alu_src = None, "profiles/r01h_detect_kernel.txt"
+    try:
+        for ln in open(os.path.join(ROOT, alu_src)):
+            if ln.startswith("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"):
+                alu_pct = float(ln.split()[-1])
+    except Exception:
+        pass
+    roofline_detect = {"bound": "hbm", "alu_pipe_active_pct_ncu": alu_pct, "alu_pipe_source": alu_src, "achieved": det_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": det_gbs / hbm_peak, "traffic": det_traffic, "peak_source": hbm_src,
                        "kernels": "detect_cm + thr + rowmask + scans + emit", "ms_per_launch": det_ms_avg,
                        "algorithmic_bytes_per_launch": det_bytes,
-                       "note": "ALU-pipe bound: the packed-u16 median network keeps the ALU pipe 81 % busy (ncu, profiles/r01c_detect_packed_kernel.txt); DRAM traffic equals the algorithmic bytes"}
+                       "note": "ALU-pipe bound, not HBM bound: the packed-u16 median network (99 compare-exchanges per pixel) keeps the ALU "
+                               "pipe 80 % busy with math_pipe_throttle as the top stall (ncu, alu_pipe_source); at the HBM roofline the "
+                               "budget would be ~6 ALU operations per pixel, below any exact 5x5 median"}
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
