@@ -530,7 +530,18 @@ def track_greedy_batch(field_frame_spots, frame_shape, candidate_radius=2, offse
     reference's order of traces; total_discarded) -- a bare tuple when one field was given."""
     L = _lib.load()
     require_cuda()
-    single = len(field_frame_spots) > 0 and (len(field_frame_spots[0]) == 0 or np.ndim(field_frame_spots[0][0]) < 2)
+    def depth(x):            # nesting depth down to the first number found (empty containers are skipped): 3 = one field
+        if isinstance(x, np.ndarray):
+            return x.ndim if x.size else None
+        if isinstance(x, (list, tuple)):
+            for e in x:
+                d = depth(e)
+                if d is not None:
+                    return d + 1
+            return None
+        return 0
+    d = depth(field_frame_spots)
+    single = (d is None) or d <= 3
     fields = [field_frame_spots] if single else list(field_frame_spots)
     n_fields = len(fields)
     F = len(fields[0])
