@@ -467,7 +467,7 @@ def run_ours(args):
                         "alone by CUDA events (one 4-warp block per SM, as launched in the pipeline: latency-bound on its own). "
                         "The kernel keeps residual / chi^2 in FP64 and the Jacobian / normal equations / Cholesky in FP32, so "
                         "the FP32 peak is an upper bound it cannot reach"}
-    alu_pct, alu_src = None, "profiles/r01h_detect_kernel.txt"
+    alu_pct, alu_src = None, "profiles/r01i_detect_kernel.txt"
     try:
         for ln in open(os.path.join(ROOT, alu_src)):
             if ln.startswith("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"):

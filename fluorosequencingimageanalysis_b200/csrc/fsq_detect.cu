@@ -529,23 +529,42 @@ extern "C" int fsq_detect(const void* frames, int dtype_code, int n_frames, int 
     static const bool allow_packed = !(getenv("FSQ_DETECT_GENERIC") && getenv("FSQ_DETECT_GENERIC")[0] == '1');
     FSQ_CUDA_CHECK(cudaMemsetAsync(sc.sums, 0, size_t(n_frames) * NSUM * 8, st));
     FSQ_CUDA_CHECK(cudaMemsetAsync(sc.flags, 0, 64, st));
-    int rc;
-    switch (dtype_code) {
-        case FSQ_U8:  rc = launch_cm<uint8_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
-        case FSQ_U16: rc = launch_cm<uint16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
-        case FSQ_I16: rc = launch_cm<int16_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
-        case FSQ_I32: rc = launch_cm<int32_t>(frames, n_frames, H, W, kp, mf_size, ksize, sc, st, allow_packed); break;
-        default:
-            set_error("fsq_detect: unsupported dtype code %d", dtype_code);
-            return FSQ_E_ARG;
+    // Pass A (correlation map + moments), the thresholds and the row masks run chunk by chunk, so that the u32 map of a
+    // chunk (4 B per pixel) is still in the 126 MB L2 when the row-mask pass reads it back: with all frames of a large
+    // batch in one go the map was written to and re-read from DRAM (37 MB instead of 22 MB of traffic per 40-frame
+    // stack, ncu).  Thresholds are per frame, so the chunking changes no result.
+    const long long px = (long long)H * W;
+    long long chunk = (64LL << 20) / (px * 6);
+    if (chunk < 1) chunk = 1;
+    const int nw = (W + 31) / 32;
+    const size_t esize = dtype_code == FSQ_U8 ? 1 : (dtype_code == FSQ_I32 ? 4 : 2);
+    for (long long f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int fc = (int)(n_frames - f0 < chunk ? n_frames - f0 : chunk);
+        DetectScratch c = sc;
+        c.cm32 = sc.cm32 + f0 * px;
+        c.sums = sc.sums + f0 * NSUM;
+        c.masks = sc.masks + f0 * H * nw;
+        c.rowcount = sc.rowcount + f0 * H;
+        const void* fr = (const char*)frames + (size_t)f0 * px * esize;
+        int rc;
+        switch (dtype_code) {
+            case FSQ_U8:  rc = launch_cm<uint8_t>(fr, fc, H, W, kp, mf_size, ksize, c, st, allow_packed); break;
+            case FSQ_U16: rc = launch_cm<uint16_t>(fr, fc, H, W, kp, mf_size, ksize, c, st, allow_packed); break;
+            case FSQ_I16: rc = launch_cm<int16_t>(fr, fc, H, W, kp, mf_size, ksize, c, st, allow_packed); break;
+            case FSQ_I32: rc = launch_cm<int32_t>(fr, fc, H, W, kp, mf_size, ksize, c, st, allow_packed); break;
+            default:
+                set_error("fsq_detect: unsupported dtype code %d", dtype_code);
+                return FSQ_E_ARG;
+        }
+        if (rc != FSQ_OK) return rc;
+        detect_thr_kernel<<<(fc + 127) / 128, 128, 0, st>>>(c.sums, fc, (long long)H * W, c_std, thr + f0, sc.flags);
+        FSQ_LAUNCH_CHECK();
+        const long long crow = (long long)fc * H;
+        detect_rowmask_kernel<<<(unsigned)((crow + 7) / 8), 256, 0, st>>>(c.cm32, thr + f0, crow, H, W, c.masks, c.rowcount);
+        FSQ_LAUNCH_CHECK();
     }
-    if (rc != FSQ_OK) return rc;
-    detect_thr_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(sc.sums, n_frames, (long long)H * W, c_std, thr, sc.flags);
-    FSQ_LAUNCH_CHECK();
     const long long nrows = (long long)n_frames * H;
     const unsigned rb = (unsigned)((nrows + 7) / 8);
-    detect_rowmask_kernel<<<rb, 256, 0, st>>>(sc.cm32, thr, nrows, H, W, sc.masks, sc.rowcount);
-    FSQ_LAUNCH_CHECK();
     detect_rowscan_kernel<<<n_frames, 256, 0, st>>>(sc.rowcount, H, sc.rowoff, n_cand);
     FSQ_LAUNCH_CHECK();
     detect_framescan_kernel<<<1, 1024, 0, st>>>(n_cand, n_frames, sc.framebase);

@@ -696,8 +696,11 @@ class FieldPipeline(object):
         self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
         self.fit_sbytes = self.L.fsq_fit_scratch_bytes(self.cap)
         self.fit_scratch = torch.empty(self.fit_sbytes, dtype=torch.uint8, device=d)
-        # cm, thr, rowmask, rowscan, framescan, emit + fit launches (FAST: prep, phase 1, phase 2 when parking, finish)
-        self.kernels_per_run = 6 + ((3 + (1 if self.opts.park_after != 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
+        # detection: (cm, thr, rowmask) per chunk of frames whose correlation map fits the L2 (fsq_detect), then rowscan,
+        # framescan, emit; + fit launches (FAST: prep, phase 1, phase 2 when parking, finish)
+        det_chunk = max(1, (64 << 20) // (self.H * self.W * 6))
+        self.kernels_per_run = 3 * (-(-self.F // det_chunk)) + 3 + \
+            ((3 + (1 if self.opts.park_after != 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
         # optional tail of find_peptides on the device: R^2 gate + consolidation + re-key (7 launches), packed
         # final PSFs in dictionary order (3 launches) -- what then leaves the device is ~1 record per spot
         self.consolidate = bool(consolidate)
