@@ -879,7 +879,7 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
 }
 
 // Persistent launch of the frame-path kernel with `warps_per_sm` warps per SM (fsq.h): block size and
-// blocks per SM are chosen so that the register budget per thread stays the same (221 registers).
+// blocks per SM are chosen so that the register budget per thread stays the same (168 registers).
 static int launch_frame_path(WarpArgs& a, unsigned long long* head, cudaStream_t st) {
     switch (a.o.warps_per_sm) {
         case 1:  return launch_warp<5, 32, 8, true>(a, 1, head, st);

@@ -106,8 +106,8 @@ typedef struct fsq_lm_opts {
                                 into 16 blocks.  Measured on B200 in the pipelined step: +4 % (four stacks per
                                 launch) to +16 % (one stack per launch); engine.FieldPipeline uses -8.
                            0 = one launch (default).                                          */
-    int32_t warps_per_sm;/* FAST solver scheduling only: warps per SM of the persistent LM launch: 8 (= 0,
-                           the default: the launch fills the machine), 4, 2 or 1.  A small value leaves
+    int32_t warps_per_sm;/* FAST solver scheduling only: warps per SM of the persistent LM launch: 0 (the
+                           default: the launch fills the machine, 12 warps per SM), 4, 2 or 1.  A small value leaves
                            most of every SM to launches queued on other streams: with several batches in
                            flight (engine.FieldStream) each thread then works through many more fits, so
                            far fewer warp-ticks are spent on half-empty warps waiting for their last long
