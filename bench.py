@@ -234,6 +234,18 @@ SOLVERS = {"fast": ("fast", False), "fast64": ("fast64", False),
 FLOP_PER_LM_ITER = {"fast": 132 * 25 + 300, "fast64": 132 * 25 + 300, "minpack": FLOP_PER_LM_ITER_5x5}
 
 
+def stacks_per_launch(steps, requested=None):
+    """How many 40-frame stacks (steps) one pass of the kernels processes: the timed regions run EXACTLY `steps` steps, so
+    the group size divides it -- 4 by default, else the nearest size that does; an explicit request is reduced to a divisor."""
+    steps = max(int(steps), 1)
+    if requested is None:
+        return next(g for g in (4, 5, 6, 8, 7, 3, 2, 1) if steps % g == 0)
+    g = max(1, min(int(requested), steps))
+    while steps % g:
+        g -= 1
+    return g
+
+
 def run_ours(args):
     import ctypes
     import torch
@@ -259,12 +271,7 @@ def run_ours(args):
     solver, faithful = SOLVERS[args.solver]
     warmup = max(args.warmup, 3)
     # ---- steps per launch: G stacks (steps) go through the kernels together; G divides the number of timed steps
-    if args.stacks_per_launch is None:            # automatic: 4 stacks per launch, else the nearest size that divides K
-        G = next(g for g in (4, 5, 6, 8, 7, 3, 2, 1) if args.steps % g == 0)
-    else:
-        G = max(1, min(args.stacks_per_launch, args.steps))
-        while args.steps % G:
-            G -= 1
+    G = stacks_per_launch(args.steps, args.stacks_per_launch)
     n_launch = args.steps // G                    # launches in each timed region: n_launch * G = args.steps steps exactly
     w_launch = max(3, -(-warmup // G))
     FL = N_FRAMES * G                             # frames per launch

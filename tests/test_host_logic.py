@@ -328,3 +328,17 @@ def test_greedy_tracking_oracle_known_answers():
     assert nd == 1 and tr == [[1, None], [None, 0]]
     with pytest.raises(ValueError):
         tro.accumulate_offsets([(1, 0), (0, 0)])
+
+
+def test_bench_groups_stacks_without_changing_the_step_count():
+    """bench.py times EXACTLY K steps (40-frame stacks); the stacks-per-launch grouping must divide K for every K."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for k in range(1, 130):
+        g = bench.stacks_per_launch(k)
+        assert 1 <= g <= 8 and k % g == 0
+        for req in (1, 3, 4, 8, 50):
+            g = bench.stacks_per_launch(k, req)
+            assert 1 <= g <= min(req, k) and k % g == 0
+    assert bench.stacks_per_launch(400) == 4 and bench.stacks_per_launch(50) == 5 and bench.stacks_per_launch(7) == 7
+    assert bench.stacks_per_launch(11) == 1 and bench.stacks_per_launch(2) == 2
