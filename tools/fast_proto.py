@@ -96,6 +96,9 @@ def tri_solve(L, okc, rhs):
     return y
 
 
+LMPAR_EXTRA, LMPAR_TICKS = [], []       # instrumentation: extra lmpar iterations per damped fit-tick; fits per tick
+
+
 def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fdt=None, maxiter=200, tr='lm',
              ftol=1e-10, xtol=1e-10, gtol=1e-10, factor=100.0, rank_eps=None, verbose=False):
     """data [N,win,win]; returns dict(params, status, niter, nfev, chi2)."""
@@ -221,7 +224,9 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fd
             prr = np.where(prr == 0, gsn / np.where(dxn > 0, dxn, 1), prr)
             run = todo.copy()
             fp_run = fp.copy()
+            cnt = np.zeros(len(idx), dtype=np.int64)            # extra lmpar iterations of this tick, per damped fit
             for k in range(10):
+                cnt += run
                 prr = np.where(run & (prr == 0), np.maximum(2.2e-308, paru * 0.001), prr)
                 M = C + prr[:, None, None] * (T[:, :, None] * np.eye(7)[None])
                 y2, L2, ok2 = chol_solve(M.astype(dt).astype(np.float64), -gs, rank_eps * 0)
@@ -244,6 +249,8 @@ def fast_fit(data, p0, lo, hi, lim_lo, lim_hi, dt=np.float64, acc=np.float64, fd
                 parl = np.where(run & (fp2 > 0), np.maximum(parl, prr), parl)
                 paru = np.where(run & (fp2 < 0), np.minimum(paru, prr), paru)
                 prr = np.where(run, np.maximum(parl, prr + parc), prr)
+            LMPAR_EXTRA.append(cnt[todo])
+        LMPAR_TICKS.append(len(idx))
         par[idx] = pr
         # ---------------- bounds, mpfit.py:1184-1231
         xi = x[idx]
@@ -347,6 +354,17 @@ def main():
             key, ok.mean(), ok[stab].mean(), stab.sum(), np.mean(r["chi2"] <= g[key + "_fnorm"][:n] * (1 + 1e-6)),
             np.mean((r["chi2"] <= g[key + "_fnorm"][:n] * (1 + 1e-6))[stab])))
     print("status", dict(zip(*np.unique(r["status"], return_counts=True))), "mean niter %.2f nfev %.2f" % (r["niter"].mean(), r["nfev"].mean()))
+    ex = np.concatenate(LMPAR_EXTRA) if LMPAR_EXTRA else np.zeros(0, dtype=np.int64)
+    ticks = int(np.sum(LMPAR_TICKS))
+    print("lmpar: %d fit-ticks, %.3f damped, extra iterations per damped tick: mean %.2f, histogram 1..10 %s" % (
+        ticks, len(ex) / max(ticks, 1), ex.mean() if len(ex) else 0, np.bincount(ex, minlength=11)[1:11].tolist()))
+    # what a warp pays: the maximum over its 32 lanes (fits drawn at random per tick)
+    rng = np.random.default_rng(0)
+    per_lane = np.zeros(ticks, dtype=np.int64)
+    per_lane[:len(ex)] = ex
+    rng.shuffle(per_lane)
+    w = per_lane[:ticks // 32 * 32].reshape(-1, 32)
+    print("       per warp-tick (32 random lanes): mean of the maximum %.2f, mean over lanes %.2f" % (w.max(axis=1).mean(), w.mean()))
     np.savez("/tmp/fast_proto_%s_%s.npz" % (a.dtype, a.acc), **r)
 
 
