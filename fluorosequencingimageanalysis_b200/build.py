@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libfsq.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
 SOURCES = ["fsq_api.cu", "fsq_detect.cu", "fsq_lmfit.cu", "fsq_lmfast.cu", "fsq_lmwarp.cu", "fsq_consolidate.cu", "fsq_track.cu"]
-HEADERS = ["fsq_common.cuh", "fsq_median.cuh", "fsq_chol7.cuh", os.path.join("..", "..", "include", "fsq.h")]
+HEADERS = ["fsq_common.cuh", "fsq_median.cuh", "fsq_median_pair.cuh", "fsq_chol7.cuh", os.path.join("..", "..", "include", "fsq.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # per-file extras.  The reference-faithful MINPACK kernel is compiled without implicit FMA

@@ -342,3 +342,17 @@ def test_bench_groups_stacks_without_changing_the_step_count():
             assert 1 <= g <= min(req, k) and k % g == 0
     assert bench.stacks_per_launch(400) == 4 and bench.stacks_per_launch(50) == 5 and bench.stacks_per_launch(7) == 7
     assert bench.stacks_per_launch(11) == 1 and bench.stacks_per_launch(2) == 2
+
+
+def test_median_pair_network_is_a_pair_of_medians_and_the_header_is_current():
+    """fsq_median_pair.cuh (the two-windows-at-once median of the packed detection kernel) is generated: the generator's
+    program must select rank 12 of each window for ALL 2^25 0/1 inputs (0-1 principle: every operation is a min or a
+    max), and the committed header must be exactly what the generator emits."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_median_pair as gmp
+    P, outs = gmp.build()
+    ops = gmp.prune(P, outs)
+    assert len(ops) == 216
+    assert gmp.verify(ops, outs)
+    committed = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_median_pair.cuh")).read()
+    assert committed == gmp.emit(ops, outs)
