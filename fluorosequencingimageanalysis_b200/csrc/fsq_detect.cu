@@ -203,12 +203,20 @@ constexpr int PTW = 64, PTH = 32;                 // output tile
 constexpr int PRW = PTW + 8, PRH = PTH + 8;       // raw tile (halo 4), PRW even
 constexpr int PMW = PTW + 4, PMH = PTH + 4;       // mf tile (halo 2)
 constexpr int PSTRIP = 8;                         // output rows per thread in the correlation stage
+#ifndef DETECT_MEDIAN_DEFAULT
+#define DETECT_MEDIAN_DEFAULT 2                   // see detect_cm_packed_kernel
+#endif
 
-template <typename PixT, bool RING, bool PAIR>
+// MEDIAN: 0 = one window pair per step (99-comparator network); 1 = two vertically adjacent window pairs per step
+// (fsq_median_pair.cuh); 2 = the same on row windows sorted once by a pre-pass into shared memory (each sorted row
+// window serves the five output rows that contain it)
+template <typename PixT, bool RING, int MEDIAN>
 __global__ void __launch_bounds__(NT)
 detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp,
                         uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums) {
+    constexpr bool PAIR = (MEDIAN == 1);
     __shared__ unsigned raw2[PRH * (PRW / 2)];        // u16 pairs
+    __shared__ unsigned srow[MEDIAN == 2 ? PRH * (PMW / 2) * 5 : 1];      // sorted 5-pixel row windows of pixel pairs
     __shared__ __align__(16) unsigned short mf[PMH * PMW];
     __shared__ unsigned long long red[4][NT / 32];
 
@@ -228,7 +236,41 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
     __syncthreads();
 
     // background removal for pixel pairs: mf = v - min(median, v); zero outside the image
-    if (PAIR) {
+    if (MEDIAN == 2) {
+        for (int idx = tid; idx < PRH * (PMW / 2); idx += NT) {               // pre-pass: sort every row window once
+            const int ry = idx / (PMW / 2), mxp = idx - ry * (PMW / 2);
+            const unsigned* row = raw2 + ry * (PRW / 2) + mxp;
+            const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
+            U16x2 r[5];
+            r[0].v = w0; r[1].v = __byte_perm(w0, w1, 0x5432); r[2].v = w1; r[3].v = __byte_perm(w1, w2, 0x5432); r[4].v = w2;
+            sort5<U16x2>(r);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) srow[idx * 5 + k] = r[k].v;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < (PMH / 2) * (PMW / 2); idx += NT) {
+            const int mp = idx / (PMW / 2), mxp = idx - mp * (PMW / 2);
+            const int my = 2 * mp, mx = 2 * mxp;
+            U16x2 p[30];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) p[i * 5 + k].v = srow[((my + i) * (PMW / 2) + mxp) * 5 + k];
+            const unsigned v_top = raw2[(my + 2) * (PRW / 2) + mxp + 1], v_bot = raw2[(my + 3) * (PRW / 2) + mxp + 1];
+            U16x2 m_top, m_bot;
+            median25_pair_sorted<U16x2>(p, m_top, m_bot);
+            unsigned out[2] = {__vsubus2(v_top, m_top.v), __vsubus2(v_bot, m_bot.v)};      // max(v - med, 0) per half
+            const int gx = tx0 - 2 + mx;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int gy = ty0 - 2 + my + q;
+                const bool yok = (gy >= 0) && (gy < H);
+                if (!(yok && gx >= 0 && gx < W)) out[q] &= 0xffff0000u;
+                if (!(yok && gx + 1 >= 0 && gx + 1 < W)) out[q] &= 0x0000ffffu;
+                *reinterpret_cast<unsigned*>(mf + (my + q) * PMW + mx) = out[q];
+            }
+        }
+    } else if (PAIR) {
         // two vertically adjacent pixel pairs per step: their windows share four of five rows, and of those 20 values
         // only the middle six can be either median -- fsq_median_pair.cuh (generated, verified on all 0/1 inputs):
         // 108 instead of 198 min/max per window
@@ -501,17 +543,13 @@ static int launch_cm(const void* frames, int F, int H, int W, const KParam& kp, 
     constexpr bool kPackable = (sizeof(PixT) <= 2) && (PixT(-1) > PixT(0));      // u8, u16
     if (kPackable && allow_packed && s == 5 && k == 5) {
         static_assert(PTW == TW && PTH == TH, "tile shapes of the two pass-A kernels must agree");
-        // developer switch (tests): FSQ_DETECT_PAIR=0 selects the one-window-per-step median (99-comparator network)
-        static const bool pair = !(getenv("FSQ_DETECT_PAIR") && getenv("FSQ_DETECT_PAIR")[0] == '0');
+        // developer switch (tests): FSQ_DETECT_PAIR = 0 / 1 / 2 selects the median formulation (see the kernel)
+        static const int median = getenv("FSQ_DETECT_PAIR") ? atoi(getenv("FSQ_DETECT_PAIR")) : DETECT_MEDIAN_DEFAULT;
         const bool ring = is_ring_template(kp);
-        if (ring && pair)
-            detect_cm_packed_kernel<PixT, true, true><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
-        else if (ring)
-            detect_cm_packed_kernel<PixT, true, false><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
-        else if (pair)
-            detect_cm_packed_kernel<PixT, false, true><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
-        else
-            detect_cm_packed_kernel<PixT, false, false><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums);
+#define FSQ_LAUNCH_PACKED(R, M) detect_cm_packed_kernel<PixT, R, M><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums)
+        if (ring) { if (median == 2) FSQ_LAUNCH_PACKED(true, 2); else if (median == 1) FSQ_LAUNCH_PACKED(true, 1); else FSQ_LAUNCH_PACKED(true, 0); }
+        else      { if (median == 2) FSQ_LAUNCH_PACKED(false, 2); else if (median == 1) FSQ_LAUNCH_PACKED(false, 1); else FSQ_LAUNCH_PACKED(false, 0); }
+#undef FSQ_LAUNCH_PACKED
     } else if (s == 5 && k == 5)
         detect_cm_kernel<PixT, 5, 5><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, s, k, sc.cm32, sc.sums);
     else

@@ -350,9 +350,7 @@ def test_median_pair_network_is_a_pair_of_medians_and_the_header_is_current():
     max), and the committed header must be exactly what the generator emits."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_median_pair as gmp
-    P, outs = gmp.build()
-    ops = gmp.prune(P, outs)
-    assert len(ops) == 216
-    assert gmp.verify(ops, outs)
+    text, n_raw, n_sorted = gmp.generate(check=True)          # raises if any 0/1 input of either window fails
+    assert (n_raw, n_sorted) == (216, 108)
     committed = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_median_pair.cuh")).read()
-    assert committed == gmp.emit(ops, outs)
+    assert committed == text

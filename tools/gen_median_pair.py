@@ -55,10 +55,12 @@ def oddeven_merge(P, w, ia, ib):
     return out
 
 
-def build():
+def build(presorted=False):
     P = Prog(30)
     w = list(range(30))                                  # wire r*5+c holds element c of row r (rows 0..5)
     for r in range(6):
+        if presorted:
+            continue                                     # the caller hands in rows that are already sorted
         for (i, j) in SORT5:
             P.ce(w, r * 5 + i, r * 5 + j)
     rows = [[r * 5 + c for c in range(5)] for r in range(6)]
@@ -87,7 +89,7 @@ def prune(P, outs):
     return keep[::-1]
 
 
-def verify(ops, outs):
+def verify(ops, outs, presorted=False):
     import numpy as np
     chunk = 1 << 21
     for which, rows in ((0, range(0, 5)), (1, range(1, 6))):
@@ -104,10 +106,36 @@ def verify(ops, outs):
                     else:
                         x = ((v >> ((r * 7 + c) % 25)) & 1).astype(np.uint8)       # arbitrary: must not matter
                     val[r * 5 + c] = x
+            if presorted:                                # sort every row first, as the kernel's pre-pass does
+                for r in range(6):
+                    for (i, j) in SORT5:
+                        a, b = val[r * 5 + i], val[r * 5 + j]
+                        val[r * 5 + i], val[r * 5 + j] = a & b, a | b
             for kind, d, a, b in ops:
                 val[d] = (val[a] & val[b]) if kind == 'min' else (val[a] | val[b])
             assert np.array_equal(val[outs[which]], (ones >= 13).astype(np.uint8)), (which, base)
     return True
+
+
+def emit_sorted(ops, outs):
+    """median25_pair_sorted: the same selection for rows that are already sorted (shared-memory pre-pass), + sort5."""
+    o = []
+    o.append("// (continued) rows pre-sorted by sort5(): %d min/max operations for both windows." % len(ops))
+    o.append("namespace fsq {")
+    o.append("template <typename V>")
+    o.append("__device__ __forceinline__ void sort5(V (&r)[5]) {")
+    for (i, j) in SORT5:
+        o.append("    { const V lo = min(r[%d], r[%d]), hi = max(r[%d], r[%d]); r[%d] = lo; r[%d] = hi; }" % (i, j, i, j, i, j))
+    o.append("}")
+    o.append("template <typename V>")
+    o.append("__device__ __forceinline__ void median25_pair_sorted(const V (&p)[30], V& top, V& bottom) {")
+    name = lambda i: ("p[%d]" % i) if i < 30 else ("t%d" % i)
+    for kind, d, a, b in ops:
+        o.append("    const V t%d = %s(%s, %s);" % (d, kind, name(a), name(b)))
+    o.append("    top = %s; bottom = %s;" % (name(outs[0]), name(outs[1])))
+    o.append("}")
+    o.append("}  // namespace fsq")
+    return "\n".join(o) + "\n"
 
 
 def emit(ops, outs):
@@ -128,10 +156,19 @@ def emit(ops, outs):
     return "\n".join(o) + "\n"
 
 
-if __name__ == "__main__":
+def generate(check=False):
     P, outs = build()
     ops = prune(P, outs)
-    if "--verify" in sys.argv:
+    P2, outs2 = build(presorted=True)
+    ops2 = prune(P2, outs2)
+    if check:
         verify(ops, outs)
-        sys.stderr.write("verified: %d operations (of %d before pruning)\n" % (len(ops), len(P.ops)))
-    sys.stdout.write(emit(ops, outs))
+        verify(ops2, outs2, presorted=True)
+    return emit(ops, outs) + emit_sorted(ops2, outs2), len(ops), len(ops2)
+
+
+if __name__ == "__main__":
+    text, n1, n2 = generate("--verify" in sys.argv)
+    if "--verify" in sys.argv:
+        sys.stderr.write("verified: %d operations (raw rows), %d (pre-sorted rows)\n" % (n1, n2))
+    sys.stdout.write(text)
