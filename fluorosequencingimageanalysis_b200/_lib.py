@@ -14,12 +14,13 @@ _c = ctypes
 _LIB = None
 
 FSQ_U8, FSQ_U16, FSQ_I16, FSQ_I32, FSQ_F64, FSQ_I64 = 0, 1, 2, 3, 4, 5
+FSQ_VERSION = 200          # include/fsq.h FSQ_VERSION this binding was written against
 FSQ_OK, FSQ_E_ARG, FSQ_E_CAPACITY, FSQ_E_CUDA, FSQ_E_RANGE = 0, -1, -2, -3, -4
 
 EXPORTED = ["fsq_version", "fsq_last_error", "fsq_detect_scratch_bytes", "fsq_detect",
             "fsq_detect_flags", "fsq_detect_copy_cm32", "fsq_lm_default_opts",
             "fsq_gaussfit_batch", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
-            "fsq_metrics", "fsq_photometry", "fsq_moments", "fsq_consolidate", "fsq_consolidate_scratch_bytes", "fsq_pack_psfs", "fsq_pack_psfs_scratch_bytes", "fsq_track_centroid", "fsq_track_greedy", "fsq_track_greedy_scratch_bytes",
+            "fsq_metrics", "fsq_illumina_s_n", "fsq_photometry", "fsq_moments", "fsq_consolidate", "fsq_consolidate_scratch_bytes", "fsq_pack_psfs", "fsq_pack_psfs_scratch_bytes", "fsq_track_centroid", "fsq_track_greedy", "fsq_track_greedy_scratch_bytes",
             "fsq_fma_peak"]
 
 
@@ -44,9 +45,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()          # raises RuntimeError when nvcc is missing
+    # build() is a sha256 comparison of the sources with the stamp of the .so when nothing changed; it rebuilds a
+    # stale library and raises when that is impossible (no nvcc), so a parity test or a benchmark can never run a
+    # binary that does not match the sources / the ABI of include/fsq.h
+    path = _build.build()
     L = _c.CDLL(path)
     vp, i32, i64, dbl = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
     L.fsq_version.restype = i32
@@ -77,6 +79,8 @@ def load():
     L.fsq_fit_scratch_bytes.argtypes = [i64]
     L.fsq_metrics.restype = i32
     L.fsq_metrics.argtypes = [vp, vp, i64, vp, vp]
+    L.fsq_illumina_s_n.restype = i32
+    L.fsq_illumina_s_n.argtypes = [vp, i64, i32, vp, vp]
     L.fsq_photometry.restype = i32
     L.fsq_photometry.argtypes = [vp, i32, i32, i32, i32, vp, vp, i64, i32, i32, i32, vp, vp]
     L.fsq_moments.restype = i32
@@ -97,6 +101,8 @@ def load():
     L.fsq_track_greedy.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, dbl, vp, vp, vp, vp, vp, vp, i64, vp]
     L.fsq_fma_peak.restype = i32
     L.fsq_fma_peak.argtypes = [i32, _c.POINTER(dbl), vp]
+    if L.fsq_version() != FSQ_VERSION:
+        raise FsqError("libfsq.so reports version %d, this package binds version %d" % (L.fsq_version(), FSQ_VERSION))
     _LIB = L
     return L
 

@@ -32,31 +32,30 @@ metrics_kernel(const long long* __restrict__ sub, const double* __restrict__ fit
     if (i >= n) return;
     const long long* s = sub + i * 25;
     const double* f = fit + i * 25;
-    long long isum = 0, imax = s[0];
-    for (int q = 0; q < 25; ++q) { isum += s[q]; imax = s[q] > imax ? s[q] : imax; }
-    const double mean = (double)isum / 25.0;
-    double ssr = 0.0, sst = 0.0;
+    long long isum = 0;
+    for (int q = 0; q < 25; ++q) isum += s[q];
+    const double mean = __ddiv_rn((double)isum, 25.0);
+    double ssr = 0.0, sst = 0.0;                    // Python sum(): unfused squares added in raster order (pflib.py:463-465, 470-472)
     for (int q = 0; q < 25; ++q) {
-        const double d = (double)s[q] - f[q];
-        ssr += d * d;
-        const double m = (double)s[q] - mean;
-        sst += m * m;
+        const double d = __dsub_rn((double)s[q], f[q]);
+        ssr = __dadd_rn(ssr, __dmul_rn(d, d));
+        const double m = __dsub_rn((double)s[q], mean);
+        sst = __dadd_rn(sst, __dmul_rn(m, m));
     }
-    // edge list order of pflib.py:278-280: rows 0 and 4, then columns 0 and 4 of rows 1..3
-    long long esum = 0;
-    for (int c = 0; c < 5; ++c) esum += s[c] + s[20 + c];
-    for (int r = 1; r < 4; ++r) esum += s[r * 5] + s[r * 5 + 4];
-    const double emean = (double)esum / 16.0;
-    double ev = 0.0;
-    for (int c = 0; c < 5; ++c) { double e = (double)s[c] - emean; ev += e * e; }
-    for (int c = 0; c < 5; ++c) { double e = (double)s[20 + c] - emean; ev += e * e; }
-    for (int r = 1; r < 4; ++r) {
-        double e = (double)s[r * 5] - emean; ev += e * e;
-        e = (double)s[r * 5 + 4] - emean; ev += e * e;
-    }
-    out[i * 3 + 0] = 1.0 - ssr / sst;
-    out[i * 3 + 1] = sqrt(ssr / 25.0);
-    out[i * 3 + 2] = ((double)imax - emean) / sqrt(ev / 16.0);
+    const double s_n = illumina_sn<5>(5, [&](int r, int c) { return s[r * 5 + c]; });   // numpy's arithmetic, bit for bit
+    out[i * 3 + 0] = __dsub_rn(1.0, __ddiv_rn(ssr, sst));
+    out[i * 3 + 1] = sqrt(__ddiv_rn(ssr, 25.0));
+    out[i * 3 + 2] = s_n;
+}
+
+// pflib.illumina_s_n for n square integer windows of any size <= 33 (pflib.py:261-281; Spot sizes are a parameter,
+// flexlibrary.py:319-320), one thread per window
+__global__ void __launch_bounds__(128)
+illumina_sn_kernel(const long long* __restrict__ sub, long long n, int size, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long* s = sub + i * size * size;
+    out[i] = illumina_sn<0>(size, [&](int r, int c) { return s[r * size + c]; });
 }
 
 __device__ __forceinline__ int load_pix_i(const void* base, int dtype, size_t off) {
@@ -368,6 +367,14 @@ using namespace fsq;
 
 extern "C" int fsq_version(void) { return FSQ_VERSION; }
 extern "C" const char* fsq_last_error(void) { return g_err; }
+
+extern "C" int fsq_illumina_s_n(const int64_t* sub, int64_t n, int size, double* out, void* stream) {
+    if (n < 0 || size < 1 || size > 33) { set_error("fsq_illumina_s_n: n >= 0 and 1 <= size <= 33 required (got %lld, %d)", (long long)n, size); return FSQ_E_ARG; }
+    if (n == 0) return FSQ_OK;
+    illumina_sn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const long long*)sub, n, size, out);
+    FSQ_LAUNCH_CHECK();
+    return FSQ_OK;
+}
 
 extern "C" int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream) {
     if (n < 0) { set_error("fsq_metrics: n < 0"); return FSQ_E_ARG; }

@@ -67,6 +67,7 @@ __device__ __forceinline__ double np_sum(int n, F f) {         // numpy pairwise
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = f(j);
     int i = 8;
+#pragma unroll 4
     for (; i < n - (n % 8); i += 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], f(i + j));
@@ -75,6 +76,33 @@ __device__ __forceinline__ double np_sum(int n, F f) {         // numpy pairwise
                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
     for (; i < n; ++i) res = __dadd_rn(res, f(i));
     return res;
+}
+
+// pflib.illumina_s_n (pflib.py:261-281) of a size x size integer window, in numpy's own arithmetic so that the value
+// is bit-identical to the reference's: (amax(sub) - mean(op)) / std(op) with op = top row, bottom row, then the
+// (h, 0), (h, -1) pairs of the middle rows (:278-280); mean(op) is exact (integers), std(op) = sqrt(add.reduce((op -
+// mean)^2) / len(op)) with add.reduce in pairwise order (np_sum; len(op) <= 128, i.e. size <= 33).  px(r, c) -> integer
+// pixel.  SIZE > 0: compile-time size (everything unrolls), SIZE == 0: run-time `size`.
+template <int SIZE, class PX>
+__device__ __forceinline__ double illumina_sn(int size_rt, PX px) {
+    const int size = SIZE > 0 ? SIZE : size_rt;
+    const int ne = 2 * size + 2 * (size > 2 ? size - 2 : 0);
+    auto edge = [&](int k) -> long long {
+        if (k < size) return px(0, k);
+        if (k < 2 * size) return px(size - 1, k - size);
+        const int kk = k - 2 * size;
+        return px(1 + kk / 2, (kk & 1) ? size - 1 : 0);
+    };
+    long long es = 0, mx = px(0, 0);
+#pragma unroll
+    for (int r = 0; r < size; ++r)
+#pragma unroll
+        for (int c = 0; c < size; ++c) { const long long v = px(r, c); mx = v > mx ? v : mx; }
+#pragma unroll
+    for (int k = 0; k < ne; ++k) es += edge(k);
+    const double mean = __ddiv_rn((double)es, (double)ne);
+    const double var_sum = np_sum(ne, [&](int k) { const double d = __dsub_rn((double)edge(k), mean); return __dmul_rn(d, d); });
+    return __ddiv_rn(__dsub_rn((double)mx, mean), sqrt(__ddiv_rn(var_sum, (double)ne)));
 }
 
 }  // namespace fsq

@@ -201,7 +201,9 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
         }
         if (!last_in) break;
     }
-    if (over) { atomicOr(&s.frame_over[ha.f], 1); deg = deg < CONS_MAXDEG ? deg : CONS_MAXDEG; }
+    // an overflowing candidate (too many rivals, or one out of int16 reach) flags its frame for cons_fallback and
+    // publishes NO rival list: a partly written list must never be walked (the scratch is uninitialised memory)
+    if (over) { atomicOr(&s.frame_over[ha.f], 1); deg = 0; }
     s.deg[a] = (unsigned char)deg;
 }
 
@@ -213,6 +215,7 @@ cons_component_kernel(ConsScratch s) {
     const long long m = *s.m_total;
     const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
     if (a >= m) return;
+    if (s.frame_over[s.hdr[a].f]) return;                      // the whole frame is redone by cons_fallback_kernel
     int member[CONS_MAXCOMP];
     int cnt = 1;
     member[0] = (int)a;

@@ -862,39 +862,33 @@ lmfit_kernel(const LmArgs a) {
             }
             if (PFLIB) {
                 // ---- pflib.py:461-473 ----
-                double ssr = 0.0, sst = 0.0, esum = 0.0;
-                long long isum = 0; int imax = -2147483647 - 1;
-                bool edge[S];
+                // in the reference's own order: Python's sum() adds the unfused squares one after another in raster
+                // order (:463-465, :470-472), illumina_s_n runs in numpy's arithmetic (fsq_common.cuh) -- pixel q of
+                // the window sits in slot q / G of lane q % G, so every lane replays the 25 terms through shuffles
+                long long isum = 0;
+#pragma unroll
+                for (int s = 0; s < S; ++s) if (valid[s]) isum += idat[s];
+#pragma unroll
+                for (int m = G / 2; m >= 1; m >>= 1) isum += __shfl_xor_sync(gmask, isum, m, G);
+                const double mean = __ddiv_rn((double)isum, 25.0);
+                double d2[S], m2[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    edge[s] = valid[s] && (px[s] == 0.0 || px[s] == 4.0 || py[s] == 0.0 || py[s] == 4.0);
-                    if (valid[s]) { isum += idat[s]; imax = max(imax, idat[s]); }
-                    if (edge[s]) esum += dat[s];
+                    const double d = __dsub_rn(dat[s], gimg[s]), m_ = __dsub_rn(dat[s], mean);
+                    d2[s] = __dmul_rn(d, d);
+                    m2[s] = __dmul_rn(m_, m_);
                 }
+                double ssr = 0.0, sst = 0.0;
+                int win[25];
 #pragma unroll
-                for (int m = G / 2; m >= 1; m >>= 1) {
-                    isum += __shfl_xor_sync(gmask, isum, m, G);
-                    imax = max(imax, __shfl_xor_sync(gmask, imax, m, G));
+                for (int q = 0; q < 25; ++q) {
+                    ssr = __dadd_rn(ssr, __shfl_sync(gmask, d2[q / G], q % G, G));
+                    sst = __dadd_rn(sst, __shfl_sync(gmask, m2[q / G], q % G, G));
+                    win[q] = __shfl_sync(gmask, idat[q / G], q % G, G);
                 }
-                esum = group_sum<G>(esum, gmask);
-                const double mean = (double)isum / 25.0, emean = esum / 16.0;
-                double evar = 0.0;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    if (valid[s]) {
-                        const double d = dat[s] - gimg[s];
-                        ssr = fma(d, d, ssr);
-                        const double m_ = dat[s] - mean;
-                        sst = fma(m_, m_, sst);
-                    }
-                    if (edge[s]) { const double e = dat[s] - emean; evar = fma(e, e, evar); }
-                }
-                ssr = group_sum<G>(ssr, gmask);
-                sst = group_sum<G>(sst, gmask);
-                evar = group_sum<G>(evar, gmask);
-                const double r_2 = 1.0 - ssr / sst;
-                const double rmse = sqrt(ssr / 25.0);
-                const double s_n = ((double)imax - emean) / sqrt(evar / 16.0);
+                const double r_2 = __dsub_rn(1.0, __ddiv_rn(ssr, sst));
+                const double rmse = sqrt(__ddiv_rn(ssr, 25.0));
+                const double s_n = illumina_sn<5>(5, [&](int r, int c) { return (long long)win[r * 5 + c]; });
                 if (g == 0) {
                     double* o = a.out_fit + idx * 12;
                     o[0] = (pf[2] + (double)cand_h) - 2.5;                   // pflib.py:461

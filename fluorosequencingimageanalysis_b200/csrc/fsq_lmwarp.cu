@@ -35,6 +35,7 @@
 #include "fsq_median.cuh"
 #include "fsq_chol7.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace fsq {
 
@@ -146,7 +147,7 @@ fit_prep_kernel(const WarpArgs a) {
     const int ch = a.cand_hw[2 * i], cw = a.cand_hw[2 * i + 1];
     const size_t fbase = (size_t)a.cand_frame[i] * a.H * a.W + (size_t)(ch - 2) * a.W + (cw - 2);
     int v[25];
-    long long isum = 0, esum = 0;
+    long long isum = 0;
     int imax = -2147483647 - 1;
 #pragma unroll
     for (int r = 0; r < 5; ++r)
@@ -155,17 +156,16 @@ fit_prep_kernel(const WarpArgs a) {
             const int p = w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
             v[r * 5 + c] = p;
             isum += p; imax = max(imax, p);
-            if (r == 0 || r == 4 || c == 0 || c == 4) esum += p;
         }
-    const double dmean = (double)isum / 25.0, emean = (double)esum / 16.0;
-    double sst = 0.0, evar = 0.0;
+    // sum((sub - mean(sub))**2) as Python's sum() forms it: exact mean, unfused squares added in raster order (pflib.py:464)
+    const double dmean = __ddiv_rn((double)isum, 25.0);
+    double sst = 0.0;
 #pragma unroll
-    for (int q = 0; q < 25; ++q) {                               // raster order (pflib.py:464)
-        const double e = (double)v[q] - dmean;
-        sst += e * e;
-        const int r = q / 5, c = q % 5;
-        if (r == 0 || r == 4 || c == 0 || c == 4) { const double e3 = (double)v[q] - emean; evar += e3 * e3; }
+    for (int q = 0; q < 25; ++q) {
+        const double e = __dsub_rn((double)v[q], dmean);
+        sst = __dadd_rn(sst, __dmul_rn(e, e));
     }
+    const double s_n = illumina_sn<5>(5, [&](int r, int c) { return (long long)v[r * 5 + c]; });   // bit-identical to pflib.illumina_s_n
     const int imed = median25<int>(v);                           // numpy.median of 25 (pflib.py:199)
     // (v[] is permuted by the selection network: re-read the window for the record)
     PrepRec rec;
@@ -180,7 +180,7 @@ fit_prep_kernel(const WarpArgs a) {
     const uint4* src = reinterpret_cast<const uint4*>(&rec);
 #pragma unroll
     for (int q = 0; q < 8; ++q) dst[q] = src[q];
-    a.out_fit[i * 12 + 9] = ((double)imax - emean) / sqrt(evar / 16.0);   // illumina_s_n, pflib.py:261-281 (final)
+    a.out_fit[i * 12 + 9] = s_n;                                          // illumina_s_n, pflib.py:261-281 (final)
 }
 
 // -------------------------------------------------------------------------------------------
@@ -846,12 +846,18 @@ long long warp_scratch_bytes(long long n) { return 64 + (long long)(sizeof(PrepR
 template <int WIN, int TPB, int MINB, bool PFLIB>
 static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
     constexpr size_t smem = (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
-    static int per_sm = 0;
+    // function attributes and occupancy are per device: cached per device ordinal (one process may drive several
+    // GPUs from several host threads -- psfio.parallel_image_batch does)
+    static std::atomic<int> per_sm_dev[64];
+    int dev = 0;
+    FSQ_CUDA_CHECK(cudaGetDevice(&dev));
+    int per_sm = (dev >= 0 && dev < 64) ? per_sm_dev[dev].load(std::memory_order_acquire) : 0;
     if (per_sm == 0) {
         FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB>, TPB, smem) != cudaSuccess || v < 1) v = 1;
         per_sm = v;
+        if (dev >= 0 && dev < 64) per_sm_dev[dev].store(v, std::memory_order_release);
     }
     const int use_per_sm = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
     long long blocks = (long long)sm_count() * use_per_sm;

@@ -432,6 +432,25 @@ def metrics_batch(sub, fit):
     return out
 
 
+def illumina_s_n_batch(sub):
+    """pflib.illumina_s_n (pflib.py:261-281) for n square integer windows [n,size,size] of any side <= 33 -> [n] f64
+    device tensor, bit-identical to the reference (numpy's summation order)."""
+    L = _lib.load()
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    a = np.asarray(sub)
+    if a.ndim == 2:
+        a = a[None]
+    if a.ndim != 3 or a.shape[1] != a.shape[2]:
+        raise ValueError("sub_img must be square, but has shape " + str(a.shape[1:]))
+    if a.dtype.kind not in "iub":
+        raise TypeError("illumina_s_n_batch takes integer pixels (the reference's sub-images are int64 copies)")
+    s = torch.from_numpy(np.ascontiguousarray(a.astype(np.int64))).to(dev)
+    out = torch.empty(s.shape[0], dtype=torch.float64, device=dev)
+    _lib.check(L.fsq_illumina_s_n(_ptr(s), s.shape[0], s.shape[1], _ptr(out), _stream()))
+    return out
+
+
 PHOT_METHODS = {"simple": 0, "mexican_hat": 1, "maximum": 2}
 
 

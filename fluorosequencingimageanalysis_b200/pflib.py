@@ -87,10 +87,9 @@ def illumina_s_n(sub_img):
     sub_img = np.asarray(sub_img)
     if not (len(sub_img.shape) == 2 and sub_img.shape[0] == sub_img.shape[1]):
         raise ValueError("sub_img must be square, but has shape " + str(sub_img))
-    if sub_img.shape[0] != 5:
-        raise NotImplementedError("the CUDA metrics kernel handles the 5x5 spots pflib/flexlibrary use")
-    out = engine.metrics_batch(sub_img[None], sub_img[None].astype(np.float64))
-    return float(out[0, 2].item())
+    if sub_img.shape[0] > 33:
+        raise NotImplementedError("fsq_illumina_s_n handles windows up to 33x33 (numpy's un-split pairwise sum)")
+    return float(engine.illumina_s_n_batch(sub_img[None])[0].item())
 
 
 def consolidate_packed(cand_hw, fit, shape, r_2_threshold=0.7, consolidation_radius=4):

@@ -165,8 +165,16 @@ def _unique_abs(paths):
     return out
 
 
+#: one device batch of image_batch holds at most this many frames / this many pixel bytes: detection scratch costs
+#: ~10 B per pixel per frame and want_fit_img 200 B per candidate, so a directory of hundreds of 2048x2048 frames
+#: must not become one launch (and a failure must not take more than one chunk's images with it)
+BATCH_MAX_FRAMES = 32
+BATCH_MAX_BYTES = 256 << 20
+
+
 def _find_peptides_many(images, params):
-    """find_peptides for a list of same-shape images through ONE device batch."""
+    """find_peptides for a list of same-shape images through ONE device batch.  -> list with, per image, either the
+    PSF dictionary or the exception that image raised (the reference loses only the failing image, pflib.py:957-996)."""
     from . import pflib, engine
     kw = dict(params)
     kw.pop('candidate_pixels', None)                     # "Not yet implemented" in the reference (pflib.py:374)
@@ -184,45 +192,63 @@ def _find_peptides_many(images, params):
     out = []
     for f, image in enumerate(images):
         sl = slice(offs[f], offs[f + 1])
-        out.append(pflib.psfs_from_packed(image, res.cand_hw[sl], res.fit[sl], res.fit_img[sl], r2t, rad))
+        try:
+            out.append(pflib.psfs_from_packed(image, res.cand_hw[sl], res.fit[sl], res.fit_img[sl], r2t, rad))
+        except Exception as e:                            # e.g. the re-key collision assert of pflib.py:518
+            out.append(e)
     return out
+
+
+def _process_chunk(chunk, params, timestamp_epoch, processed, logger):
+    """One bounded device batch of same-shape images -> result files.  If the batch as a whole fails, every image of
+    it is retried on its own, so that only the failing image is logged and skipped (the reference's granularity)."""
+    try:
+        all_psfs = _find_peptides_many([g[2] for g in chunk], params)
+    except Exception as e:
+        if len(chunk) == 1:
+            logger.exception(e, exc_info=True)
+            return
+        for item in chunk:
+            _process_chunk([item], params, timestamp_epoch, processed, logger)
+        return
+    for (orig, converted, image), psfs in zip(chunk, all_psfs):
+        try:
+            if isinstance(psfs, Exception):
+                raise psfs
+            pkl = save_psfs_pkl(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
+            csvp = save_psfs_csv(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
+            png = save_psfs_png(psfs, image_path=converted, timestamp_epoch=timestamp_epoch, image=image)
+        except Exception as e:
+            logger.exception(e, exc_info=True)
+            continue
+        processed.setdefault(orig, (converted, pkl, csvp, png))
 
 
 def image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None):
     """pflib.py:883-997 -> {original_path: (converted_path, pkl_path, csv_path, png_path)}.
-    Per-image failures are logged and skipped, as in the reference."""
+    Per-image failures are logged and skipped, as in the reference.  Images are read lazily and go to the device in
+    bounded chunks of one shape (BATCH_MAX_FRAMES / BATCH_MAX_BYTES), so host and device memory do not grow with the
+    length of the list."""
     logger = logging.getLogger()
     if timestamp_epoch is None:
         timestamp_epoch = _py2_round(time.time())
     image_paths = _unique_abs(image_paths)
     params = dict(find_peptides_parameters or {})
-    loaded = []
+    processed = {}
+    pending = {}                                          # (shape, dtype) -> images read but not yet processed
     for p in image_paths:
         try:
             converted, image = read_image(p)
         except Exception as e:
             logger.exception(e, exc_info=True)
             continue
-        loaded.append((p, converted, image))
-    by_shape = {}
-    for item in loaded:
-        by_shape.setdefault((item[2].shape, item[2].dtype.str), []).append(item)
-    processed = {}
-    for group in by_shape.values():
-        try:
-            all_psfs = _find_peptides_many([g[2] for g in group], params)
-        except Exception as e:
-            logger.exception(e, exc_info=True)
-            continue
-        for (orig, converted, image), psfs in zip(group, all_psfs):
-            try:
-                pkl = save_psfs_pkl(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
-                csvp = save_psfs_csv(psfs, image_path=converted, timestamp_epoch=timestamp_epoch)
-                png = save_psfs_png(psfs, image_path=converted, timestamp_epoch=timestamp_epoch, image=image)
-            except Exception as e:
-                logger.exception(e, exc_info=True)
-                continue
-            processed.setdefault(orig, (converted, pkl, csvp, png))
+        key = (image.shape, image.dtype.str)
+        chunk = pending.setdefault(key, [])
+        chunk.append((p, converted, image))
+        if len(chunk) >= BATCH_MAX_FRAMES or len(chunk) * image.nbytes >= BATCH_MAX_BYTES:
+            _process_chunk(pending.pop(key), params, timestamp_epoch, processed, logger)
+    for chunk in pending.values():
+        _process_chunk(chunk, params, timestamp_epoch, processed, logger)
     return processed
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FSQ_VERSION 100            /* 0.1.0 */
+#define FSQ_VERSION 200            /* 0.2.0 */
 
 #define FSQ_OK          0
 #define FSQ_E_ARG      -1          /* bad argument (NULL pointer, even kernel size, unsupported dtype ...) */
@@ -289,6 +289,11 @@ int fsq_track_greedy(const double* spot_hw, const int32_t* seg_start, const doub
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);
+
+/* pflib.illumina_s_n (pflib.py:261-281) for n square windows of any side 1..33 (Spot sizes are a parameter,
+ * flexlibrary.py:319-320): sub [n,size,size] int64 -> out [n] float64, in numpy's own summation order, so the value
+ * is bit-identical to the reference's */
+int fsq_illumina_s_n(const int64_t* sub, int64_t n, int size, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Photometry on spots -- flexlibrary.Spot.photometry family (flexlibrary.py:160-210, 264-284)

@@ -139,10 +139,24 @@ def make_detect():
         print("detect", name, img.shape, len(cands), repr(float(thr)))
 
 
-def make_fits5(procs):
+FITS5_CASES = {
+    # name: (frame factory, candidate filter or None) -- every BASELINE config's spot density has reference fits
+    "seed0": (lambda: synth.synth_frame(0), None),                                  # configs[0]/[1]
+    "seed3": (lambda: synth.synth_frame(3), None),                                  # second seed
+    "dense1000": (lambda: synth.synth_frame(11, n_spots=1000), None),               # configs[2]/[4] density
+    # configs[3]: the 2048x2048 / 20 000-spot frame; every candidate inside a 320x320 region (the frame is
+    # regenerated by the tests from the seed and checked against img_sha, 8 MB is too large to commit)
+    "d2048": (lambda: synth.synth_frame(4, H=2048, W=2048, n_spots=20000),
+              lambda h, w: 800 <= h < 1120 and 800 <= w < 1120),
+}
+
+
+def make_fits5(procs, name="seed0"):
     pflib, _, _ = ref()
-    img = synth.synth_frame(0)
-    cands = pflib._psf_candidates(img)
+    factory, keep = FITS5_CASES[name]
+    img = factory()
+    all_cands = pflib._psf_candidates(img)
+    cands = [c for c in all_cands if keep is None or keep(*c)]
     subs = [img[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in cands]
     t = time.time()
     with multiprocessing.Pool(procs) as pool:
@@ -154,7 +168,8 @@ def make_fits5(procs):
     d = _stack(rows, names)
     # the reference's full pipeline on the same frame (consolidation + re-key) -- one more
     # pass would cost 500 s, so rebuild it from the per-candidate reference answers with the
-    # restated consolidation (checked equal to the reference's on a sub-frame below)
+    # restated consolidation (checked equal to the reference's on a sub-frame below).  For a region
+    # sample the consolidation runs over the sampled candidates only (the tests do the same).
     bins = {}
     for (h, w), row in zip(cands, rows):
         p = row[0]
@@ -164,16 +179,17 @@ def make_fits5(procs):
                         row[16], row[15], row[17])
     final = po.consolidate(bins, img.shape, 4)
     keys = np.array(sorted(final.keys()), dtype=np.int32).reshape(-1, 2)
-    np.savez_compressed(os.path.join(GOLD, "fits5_seed0.npz"), img_sha=sha(img),
-                        cands=np.array(cands, dtype=np.int32), final_keys=keys,
+    np.savez_compressed(os.path.join(GOLD, "fits5_%s.npz" % name), img_sha=sha(img),
+                        cands=np.array(cands, dtype=np.int32), n_cands_frame=len(all_cands),
+                        final_keys=keys,
                         final_h0=np.array([final[tuple(k)][0] for k in keys]),
                         final_w0=np.array([final[tuple(k)][1] for k in keys]),
                         ref_seconds_total=dt, procs=procs, **d)
     st, cnt = np.unique(d["ref_status"], return_counts=True)
-    print("fits5: %d fits in %.1f s on %d procs; status %s; oracle==ref %d/%d; robust(n_qrsolv==0) %d; "
-          "accepted %d; final %d" % (len(rows), dt, procs, dict(zip(st.tolist(), cnt.tolist())),
+    print("fits5_%s: %d fits in %.1f s on %d procs; status %s; oracle==ref %d/%d; robust(n_qrsolv==0) %d; "
+          "accepted %d; final %d" % (name, len(rows), dt, procs, dict(zip(st.tolist(), cnt.tolist())),
                                      int(d["oracle_equals_ref"].sum()), len(rows),
-                                     int((d["n_qrsolv"] == 0).sum()), len(bins), len(final)))
+                                     int((d["n_qrsolv"] == 0).sum()), len(bins), len(final)), flush=True)
 
 
 def make_pipeline_small():
@@ -197,20 +213,29 @@ def make_pipeline_small():
     print("pipeline_small: %d psfs in %.1f s; oracle find_peptides identical" % (len(keys), dt))
 
 
-def make_fits11(procs):
-    img, cr, cc, amp = synth.synth_frame_with_truth(0)
-    wins = synth.cut_windows(img, cr, cc, 11)[:200]
+def _fits11_windows(name):
+    if name == "seed0":                       # configs[0]: windows around isolated spots
+        img, cr, cc, amp = synth.synth_frame_with_truth(0)
+        return synth.cut_windows(img, cr, cc, 11)[:200]
+    if name == "d2048":                       # configs[3]: windows cut from the dense 2048^2 / 20 000-spot frame
+        img, cr, cc, amp = synth.synth_frame_with_truth(4, H=2048, W=2048, n_spots=20000)
+        return synth.cut_windows(img, cr, cc, 11)[:400]
+    raise KeyError(name)
+
+
+def make_fits11(procs, name="seed0"):
+    wins = _fits11_windows(name)
     with multiprocessing.Pool(procs) as pool:
         rows = pool.map(_fit11, list(wins), chunksize=8)
     names = ["ref_params", "ref_perror", "ref_status", "ref_niter", "ref_nfev", "ref_fnorm",
              "n_qrsolv", "n_reject", "clean_params", "clean_status", "clean_niter", "clean_nfev",
              "clean_fnorm", "oracle_equals_ref", "p0"]
     d = _stack(rows, names)
-    np.savez_compressed(os.path.join(GOLD, "fits11_seed0.npz"), windows=wins, **d)
+    np.savez_compressed(os.path.join(GOLD, "fits11_%s.npz" % name), windows=wins, **d)
     st, cnt = np.unique(d["ref_status"], return_counts=True)
-    print("fits11: %d; status %s; oracle==ref %d; robust %d" % (
-        len(rows), dict(zip(st.tolist(), cnt.tolist())), int(d["oracle_equals_ref"].sum()),
-        int((d["n_qrsolv"] == 0).sum())))
+    print("fits11_%s: %d; status %s; oracle==ref %d; robust %d" % (
+        name, len(rows), dict(zip(st.tolist(), cnt.tolist())), int(d["oracle_equals_ref"].sum()),
+        int((d["n_qrsolv"] == 0).sum())), flush=True)
 
 
 if __name__ == "__main__":
@@ -227,10 +252,12 @@ if __name__ == "__main__":
         make_detect()
     if "pipeline_small" in todo:
         make_pipeline_small()
-    if "fits11" in todo:
-        make_fits11(a.procs)
-    if "fits5" in todo:
-        make_fits5(a.procs)
+    for t_ in todo:                            # fits11[:case], fits5[:case]
+        kind, _, case = t_.partition(":")
+        if kind == "fits11":
+            make_fits11(a.procs, case or "seed0")
+        if kind == "fits5":
+            make_fits5(a.procs, case or "seed0")
 
 
 # ----------------------------------------------------------------------------- phase_correlate (reference run)

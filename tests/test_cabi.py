@@ -24,7 +24,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     L = _lib.load()
-    assert L.fsq_version() == 100
+    assert L.fsq_version() == _lib.FSQ_VERSION == 200
 
 
 def test_every_declared_symbol_is_exported():
