@@ -715,11 +715,11 @@ class FieldPipeline(object):
         self.out_int = torch.empty((self.cap, 4), dtype=torch.int32, device=d)
         self.fit_sbytes = self.L.fsq_fit_scratch_bytes(self.cap)
         self.fit_scratch = torch.empty(self.fit_sbytes, dtype=torch.uint8, device=d)
+        self.F_run = self.F
+        self.consolidate = False
         # detection: (cm, thr, rowmask) per chunk of frames whose correlation map fits the L2 (fsq_detect), then rowscan,
         # framescan, emit; + fit launches (FAST: prep, phase 1, phase 2 when parking, finish)
-        det_chunk = max(1, (64 << 20) // (self.H * self.W * 6))
-        self.kernels_per_run = 3 * (-(-self.F // det_chunk)) + 3 + \
-            ((3 + (1 if self.opts.park_after != 0 else 0)) if _lib.SOLVERS[solver] == 2 else 1)
+        self.kernels_per_run = self.launches_per_run()
         # optional tail of find_peptides on the device: R^2 gate + consolidation + re-key (7 launches), packed
         # final PSFs in dictionary order (3 launches) -- what then leaves the device is ~1 record per spot
         self.consolidate = bool(consolidate)
@@ -738,36 +738,49 @@ class FieldPipeline(object):
             self.psf_fit = torch.empty((self.cap_psf, 12), dtype=torch.float64, device=d)
             self.psf_int = torch.empty((self.cap_psf, 4), dtype=torch.int32, device=d)
             self.psf_base = torch.zeros(self.F + 1, dtype=torch.int64, device=d)
-            self.kernels_per_run += 10
+            self.kernels_per_run = self.launches_per_run()
 
-    def run(self, frames_dev, fit=True):
-        """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype)."""
+    def launches_per_run(self, n_frames=None):
+        """Kernel launches one run() enqueues for ``n_frames`` frames (bench.py's gpu_launches)."""
+        F = self.F if n_frames is None else int(n_frames)
+        det_chunk = max(1, (64 << 20) // (self.H * self.W * 6))
+        k = 3 * (-(-F // det_chunk)) + 3 + \
+            ((3 + (1 if self.opts.park_after != 0 else 0)) if _lib.SOLVERS[self.solver] == 2 else 1)
+        return k + (10 if self.consolidate else 0)
+
+    def run(self, frames_dev, fit=True, n_frames=None):
+        """Enqueue one pass over frames_dev [F,H,W] (device tensor of self.dtype).  ``n_frames`` <= the F the
+        pipeline was sized for runs a partial batch through the same buffers (the last chunk of a field block)."""
         L = self.L
+        F = self.F if n_frames is None else int(n_frames)
+        if not (1 <= F <= self.F) or frames_dev.shape[0] < F:
+            raise ValueError("n_frames must be in 1..%d and covered by frames_dev" % self.F)
+        self.F_run = F
         Kp = self.K.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
         st = _stream()
-        _lib.check(L.fsq_detect(_ptr(frames_dev), self.code, self.F, self.H, self.W, Kp, self.K.shape[0],
+        _lib.check(L.fsq_detect(_ptr(frames_dev), self.code, F, self.H, self.W, Kp, self.K.shape[0],
                                 self.mf, self.c_std, _ptr(self.cand_hw), _ptr(self.cand_frame),
                                 _ptr(self.n_cand), _ptr(self.thr), self.cap, _ptr(self.scratch),
                                 self.sbytes, st))
         if fit:
-            n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * self.F)
-            _lib.check(L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
+            n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * F)
+            _lib.check(L.fsq_fit_candidates(_ptr(frames_dev), self.code, F, self.H, self.W,
                                             _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
                                             ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
                                             None, _ptr(self.fit_scratch), self.fit_sbytes, st))
             if self.consolidate:
                 _lib.check(L.fsq_consolidate(_ptr(self.cand_hw), _ptr(self.cand_frame), _ptr(self.out_fit), self.cap, n_dev,
-                                             self.F, self.r2_thr, self.radius, _ptr(self.psf_state), _ptr(self.psf_key),
+                                             F, self.r2_thr, self.radius, _ptr(self.psf_state), _ptr(self.psf_key),
                                              _ptr(self.n_psf), _ptr(self.cons_flags), _ptr(self.cons_scratch),
                                              self.cons_sbytes, st))
                 _lib.check(L.fsq_pack_psfs(_ptr(self.psf_state), _ptr(self.psf_key), _ptr(self.cand_frame), _ptr(self.out_fit),
-                                           self.cap, n_dev, self.F, _ptr(self.psf_fit), _ptr(self.psf_int), _ptr(self.psf_base),
+                                           self.cap, n_dev, F, _ptr(self.psf_fit), _ptr(self.psf_int), _ptr(self.psf_base),
                                            self.cap_psf, _ptr(self.cons_scratch), self.cons_sbytes, st))
 
     def total_psfs(self):
         """Synchronising read of the number of final PSFs; raises if the PSF capacity was exceeded or the
         reference's re-key assert (pflib.py:518) would have fired."""
-        m = int(self.psf_base[self.F].item())
+        m = int(self.psf_base[self.F_run].item())
         if m > self.cap_psf:
             raise _lib.FsqError("capacity: %d PSFs > cap %d; enlarge cap_psf_per_frame" % (m, self.cap_psf))
         check_consolidation_flags(int(self.cons_flags.item()))
@@ -777,22 +790,22 @@ class FieldPipeline(object):
         """-> (m, psf_int [m,4] (frame, key_h, key_w, candidate index), psf_fit [m,12], psf_base [F+1]) on the host"""
         self.total()
         m = self.total_psfs()
-        return m, self.psf_int[:m].cpu(), self.psf_fit[:m].cpu(), self.psf_base.cpu()
+        return m, self.psf_int[:m].cpu(), self.psf_fit[:m].cpu(), self.psf_base[:self.F_run + 1].cpu()
 
     def run_detect_only(self, frames_dev):
         self.run(frames_dev, fit=False)
 
     def run_fit_only(self, frames_dev):
         """Re-fit the candidates of the last detection (used to time the fit kernel alone)."""
-        n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * self.F)
-        _lib.check(self.L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F, self.H, self.W,
+        n_dev = ctypes.c_void_p(self.n_cand.data_ptr() + 8 * self.F_run)
+        _lib.check(self.L.fsq_fit_candidates(_ptr(frames_dev), self.code, self.F_run, self.H, self.W,
                                              _ptr(self.cand_hw), _ptr(self.cand_frame), self.cap, n_dev,
                                              ctypes.byref(self.opts), _ptr(self.out_fit), _ptr(self.out_int),
                                              None, _ptr(self.fit_scratch), self.fit_sbytes, _stream()))
 
     def total(self):
         """Synchronising read of the candidate total; raises if the capacity was exceeded."""
-        n = int(self.n_cand[self.F].item())
+        n = int(self.n_cand[self.F_run].item())
         if n > self.cap:
             raise _lib.FsqError("capacity: %d candidates > cap %d; enlarge cap_per_frame" % (n, self.cap))
         return n
@@ -864,24 +877,34 @@ class FieldStream(object):
             self.slots.append(sl)
         self.k = 0
         self.kernels_per_run = self.slots[0]["pipe"].kernels_per_run
+        # host -> device frame copies go through ONE dedicated stream, in submission order: a copy queued on a slot's own
+        # stream shares a hardware work queue with other slots' kernels (CUDA maps streams onto a few queues) and holds
+        # them back -- measured on B200: the e2e region ran 12-16 % below the resident one with per-slot copies
+        self.copy_stream = torch.cuda.Stream(device=self.slots[0]["pipe"].dev) if host_io else None
 
     def submit(self, frames):
+        """frames: [F', H, W] with F' <= the batch size the stream was built for (a shorter last chunk is allowed)"""
         sl = self.slots[self.k % self.depth]
         self.k += 1
         p = sl["pipe"]
+        F = int(frames.shape[0])
         sl["stream"].wait_stream(torch.cuda.current_stream())
+        if frames.device.type == "cpu":
+            self.copy_stream.wait_stream(sl["stream"])          # the slot's previous batch has finished with frames_dev
+            with torch.cuda.stream(self.copy_stream):
+                sl["frames_dev"][:F].copy_(frames, non_blocking=True)
+            sl["stream"].wait_stream(self.copy_stream)
+            frames = sl["frames_dev"]
         with torch.cuda.stream(sl["stream"]):
-            if frames.device.type == "cpu":
-                sl["frames_dev"].copy_(frames, non_blocking=True)
-                frames = sl["frames_dev"]
-            p.run(frames)
+            p.run(frames, n_frames=F)
             if self.host_io:
-                sl["count_host"][0:1].copy_(p.n_cand[p.F:p.F + 1], non_blocking=True)
+                sl["count_host"][0:1].copy_(p.n_cand[F:F + 1], non_blocking=True)
                 if self.fetch == "psfs":
-                    sl["count_host"][1:2].copy_(p.psf_base[p.F:p.F + 1], non_blocking=True)
+                    sl["count_host"][1:2].copy_(p.psf_base[F:F + 1], non_blocking=True)
                     sl["pinned"]["flags"].copy_(p.cons_flags, non_blocking=True)
                 sl["ev_count"].record(sl["stream"])
         sl["n"] = None
+        sl["F"] = F
         return sl
 
     def begin_fetch(self, sl):
@@ -899,7 +922,7 @@ class FieldStream(object):
             with torch.cuda.stream(sl["stream"]):
                 pin["psf_fit"][:m].copy_(p.psf_fit[:m], non_blocking=True)
                 pin["psf_int"][:m].copy_(p.psf_int[:m], non_blocking=True)
-                pin["psf_base"].copy_(p.psf_base, non_blocking=True)
+                pin["psf_base"][:sl["F"] + 1].copy_(p.psf_base[:sl["F"] + 1], non_blocking=True)
                 sl["ev_done"].record(sl["stream"])
             sl["n"], sl["m"] = n, m
             return n
@@ -919,7 +942,7 @@ class FieldStream(object):
         n, pin = sl["n"], sl["pinned"]
         if self.fetch == "psfs":        # (candidates fitted, final PSFs, psf_int [m,4], psf_fit [m,12], psf_base [F+1])
             m = sl["m"]
-            return n, m, pin["psf_int"][:m], pin["psf_fit"][:m], pin["psf_base"]
+            return n, m, pin["psf_int"][:m], pin["psf_fit"][:m], pin["psf_base"][:sl["F"] + 1]
         return n, pin["hw"][:n], pin["frame"][:n], pin["fit"][:n], pin["ints"][:n]
 
     def synchronize(self):

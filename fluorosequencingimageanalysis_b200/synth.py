@@ -79,6 +79,27 @@ def synth_experiment(seed, n_fields=100, n_cycles=10, H=512, W=512, n_spots=1000
     return out
 
 
+def dihedral_variants(stack):
+    """The 8 symmetries of the square applied to the last two axes of ``stack`` [..., H, H] -> list of 8 arrays.
+    A flipped / transposed synthetic frame is again a synthetic frame of the same recipe (isotropic spots, i.i.d.
+    noise), so a few generated fields give 8x as many different ones for the cost of a copy (bench.py's frame pool)."""
+    if stack.shape[-1] != stack.shape[-2]:
+        raise ValueError("dihedral variants need square frames")
+    out = []
+    for t in (stack, np.swapaxes(stack, -1, -2)):
+        out += [t, t[..., ::-1, :], t[..., :, ::-1], t[..., ::-1, ::-1]]
+    return [np.ascontiguousarray(v) for v in out]
+
+
+def experiment_field_pool(seed, n_fields, n_cycles=10, H=512, W=512, n_spots=1000, **kw):
+    """[n_fields, n_cycles, H, W] uint16: ceil(n_fields / 8) fields by synth_experiment (config 3 / 5 recipe), the
+    rest their dihedral variants."""
+    n_base = -(-n_fields // 8)
+    base = synth_experiment(seed, n_fields=n_base, n_cycles=n_cycles, H=H, W=W, n_spots=n_spots, **kw)
+    pool = np.concatenate(dihedral_variants(base), axis=0) if H == W else np.concatenate([base] * 8, axis=0)
+    return pool[:n_fields]
+
+
 def cut_windows(frame, cr, cc, win=11):
     """Pre-cut win x win float64 windows centred on the rounded true centres
     (the direct-gaussfit 11x11 variant of config 1 / config 4)."""

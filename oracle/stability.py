@@ -86,55 +86,71 @@ def ensemble(pool, jobs, K):
     return out
 
 
+def stability5(pool, name, K, keep_ensemble):
+    """stable flags of the 5x5 golden case `name` (oracle/make_golden.py FITS5_CASES) -> tests/golden/stable5_<name>.npz"""
+    from oracle import make_golden
+    g5 = dict(np.load(os.path.join(GOLD, "fits5_%s.npz" % name)))
+    img = make_golden.FITS5_CASES[name][0]()
+    assert make_golden.sha(img) == str(g5["img_sha"])
+    subs = [img[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in g5["cands"]]
+    res = {}
+    for faithful, key in ((True, "ref"), (False, "clean")):
+        jobs = []
+        for s in subs:
+            p, lmin, lmax, mn, mx = po.pflib_fit_args(s)
+            jobs.append((s, p, (lmin, lmax, mn, mx), faithful))
+        ens = ensemble(pool, jobs, K)
+        base_p, base_s = g5[key + "_params"], g5[key + "_status"]
+        stable = np.ones(len(subs), dtype=bool)
+        for P, S, _ in ens:
+            stable &= agree(P, base_p)
+            if faithful:
+                stable &= (S == base_s)
+        res["stable_" + key] = stable
+        if keep_ensemble:
+            # float32 is ample for the 1e-4 agreement test and keeps the fixture small
+            res["ens_params_" + key] = np.stack([e[0] for e in ens]).astype(np.float32)
+            res["ens_status_" + key] = np.stack([e[1] for e in ens]).astype(np.int8)
+        res["ens_agree_" + key] = np.stack([agree(e[0], base_p) & ((e[1] == base_s) if faithful else True)
+                                            for e in ens])
+        print("5x5 %s %s: stable %d of %d (%.1f %%)" % (name, key, stable.sum(), len(stable), 100 * stable.mean()), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "stable5_%s.npz" % name), k=K, **res)
+
+
+def stability11(pool, name, K):
+    g11 = dict(np.load(os.path.join(GOLD, "fits11_%s.npz" % name)))
+    res = {}
+    lims = (po.GAUSSFIT_DEFAULT_LIMITEDMIN, po.GAUSSFIT_DEFAULT_LIMITEDMAX,
+            po.GAUSSFIT_DEFAULT_MINPARS, po.GAUSSFIT_DEFAULT_MAXPARS)
+    for faithful, key in ((True, "ref"), (False, "clean")):
+        jobs = [(w, p0, lims, faithful) for w, p0 in zip(g11["windows"], g11["p0"])]
+        ens = ensemble(pool, jobs, K)
+        stable = np.ones(len(jobs), dtype=bool)
+        for P, S, _ in ens:
+            stable &= agree(P, g11[key + "_params"])
+            if faithful:
+                stable &= (S == g11[key + "_status"])
+        res["stable_" + key] = stable
+        res["ens_agree_" + key] = np.stack([agree(e[0], g11[key + "_params"]) &
+                                            ((e[1] == g11[key + "_status"]) if faithful else True)
+                                            for e in ens])
+        print("11x11 %s %s: stable %d of %d" % (name, key, stable.sum(), len(stable)), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "stable11_%s.npz" % name), k=K, **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--cases", default="5:seed0,11:seed0", help="comma list of 5:<case> / 11:<case> (make_golden case names)")
     a = ap.parse_args()
-    g5 = dict(np.load(os.path.join(GOLD, "fits5_seed0.npz")))
-    img = synth.synth_frame(0)
-    subs = [img[h - 2:h + 3, w - 2:w + 3].astype(np.int64) for h, w in g5["cands"]]
     with multiprocessing.Pool(a.procs) as pool:
-        res = {}
-        for faithful, key in ((True, "ref"), (False, "clean")):
-            jobs = []
-            for s in subs:
-                p, lmin, lmax, mn, mx = po.pflib_fit_args(s)
-                jobs.append((s, p, (lmin, lmax, mn, mx), faithful))
-            ens = ensemble(pool, jobs, a.k)
-            base_p, base_s = g5[key + "_params"], g5[key + "_status"]
-            stable = np.ones(len(subs), dtype=bool)
-            for P, S, _ in ens:
-                stable &= agree(P, base_p)
-                if faithful:
-                    stable &= (S == base_s)
-            res["stable_" + key] = stable
-            # float32 is ample for the 1e-4 agreement test and keeps the fixture small
-            res["ens_params_" + key] = np.stack([e[0] for e in ens]).astype(np.float32)
-            res["ens_status_" + key] = np.stack([e[1] for e in ens]).astype(np.int8)
-            res["ens_agree_" + key] = np.stack([agree(e[0], base_p) & ((e[1] == base_s) if faithful else True)
-                                                for e in ens])
-            print("5x5 %s: stable %d of %d (%.1f %%)" % (key, stable.sum(), len(stable), 100 * stable.mean()))
-        np.savez_compressed(os.path.join(GOLD, "stable5_seed0.npz"), k=a.k, **res)
-
-        g11 = dict(np.load(os.path.join(GOLD, "fits11_seed0.npz")))
-        res = {}
-        lims = (po.GAUSSFIT_DEFAULT_LIMITEDMIN, po.GAUSSFIT_DEFAULT_LIMITEDMAX,
-                po.GAUSSFIT_DEFAULT_MINPARS, po.GAUSSFIT_DEFAULT_MAXPARS)
-        for faithful, key in ((True, "ref"), (False, "clean")):
-            jobs = [(w, p0, lims, faithful) for w, p0 in zip(g11["windows"], g11["p0"])]
-            ens = ensemble(pool, jobs, a.k)
-            stable = np.ones(len(jobs), dtype=bool)
-            for P, S, _ in ens:
-                stable &= agree(P, g11[key + "_params"])
-                if faithful:
-                    stable &= (S == g11[key + "_status"])
-            res["stable_" + key] = stable
-            res["ens_agree_" + key] = np.stack([agree(e[0], g11[key + "_params"]) &
-                                                ((e[1] == g11[key + "_status"]) if faithful else True)
-                                                for e in ens])
-            print("11x11 %s: stable %d of %d" % (key, stable.sum(), len(stable)))
-        np.savez_compressed(os.path.join(GOLD, "stable11_seed0.npz"), k=a.k, **res)
+        for c in a.cases.split(","):
+            kind, name = c.split(":")
+            if kind == "5":
+                stability5(pool, name, a.k, keep_ensemble=(name == "seed0"))
+            else:
+                stability11(pool, name, a.k)
 
 
 if __name__ == "__main__":

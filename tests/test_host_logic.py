@@ -330,18 +330,34 @@ def test_greedy_tracking_oracle_known_answers():
         tro.accumulate_offsets([(1, 0), (0, 0)])
 
 
-def test_bench_groups_stacks_without_changing_the_step_count():
-    """bench.py times EXACTLY K steps (40-frame stacks); the stacks-per-launch grouping must divide K for every K."""
+def test_bench_partition_covers_every_field_of_a_step_exactly_once():
+    """bench.py's strong-scaling plan: sharding.balanced_field_blocks splits a step's 800 fields into contiguous blocks
+    with near-equal candidate totals; plan_chunks turns a block into launches of <= LAUNCH_FIELDS consecutive fields,
+    each one contiguous slice of the (wrapped) frame pool.  Every field is processed exactly once for any world size."""
     sys.path.insert(0, ROOT)
     import bench
-    for k in range(1, 130):
-        g = bench.stacks_per_launch(k)
-        assert 1 <= g <= 8 and k % g == 0
-        for req in (1, 3, 4, 8, 50):
-            g = bench.stacks_per_launch(k, req)
-            assert 1 <= g <= min(req, k) and k % g == 0
-    assert bench.stacks_per_launch(400) == 4 and bench.stacks_per_launch(50) == 5 and bench.stacks_per_launch(7) == 7
-    assert bench.stacks_per_launch(11) == 1 and bench.stacks_per_launch(2) == 2
+    from fluorosequencingimageanalysis_b200 import sharding
+    rng = np.random.default_rng(3)
+    pool_counts = rng.integers(50000, 70000, bench.POOL_FIELDS)
+    step_counts = pool_counts[np.arange(bench.FIELDS_PER_STEP) % bench.POOL_FIELDS]
+    for world in (1, 2, 3, 4, 8):
+        blocks = sharding.balanced_field_blocks(step_counts, world)
+        assert blocks[0][0] == 0 and blocks[-1][1] == bench.FIELDS_PER_STEP
+        seen = np.zeros(bench.FIELDS_PER_STEP, dtype=int)
+        tot = []
+        for lo, hi in blocks:
+            f = lo
+            for p0, nf in bench.plan_chunks(lo, hi):
+                assert 1 <= nf <= bench.LAUNCH_FIELDS and 0 <= p0 < bench.POOL_FIELDS
+                assert p0 == f % bench.POOL_FIELDS and p0 + nf <= bench.POOL_FIELDS + bench.LAUNCH_FIELDS
+                seen[f:f + nf] += 1
+                f += nf
+            assert f == hi
+            tot.append(step_counts[lo:hi].sum())
+        assert (seen == 1).all()
+        assert max(tot) - min(tot) <= 2 * step_counts.max()          # balanced to within a field or two
+    cfg1, cfg8 = bench.static_config(1), bench.static_config(8)
+    assert cfg1["workload"] == cfg8["workload"] and cfg1["frames_per_step"] == 8000
 
 
 def test_median_pair_network_is_a_pair_of_medians_and_the_header_is_current():
