@@ -19,7 +19,7 @@ FSQ_OK, FSQ_E_ARG, FSQ_E_CAPACITY, FSQ_E_CUDA, FSQ_E_RANGE = 0, -1, -2, -3, -4
 
 EXPORTED = ["fsq_version", "fsq_last_error", "fsq_detect_scratch_bytes", "fsq_detect",
             "fsq_detect_flags", "fsq_detect_copy_cm32", "fsq_lm_default_opts",
-            "fsq_gaussfit_batch", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
+            "fsq_gaussfit_batch", "fsq_gaussfit_batch_ex", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
             "fsq_metrics", "fsq_illumina_s_n", "fsq_photometry", "fsq_moments", "fsq_consolidate", "fsq_consolidate_scratch_bytes", "fsq_pack_psfs", "fsq_pack_psfs_scratch_bytes", "fsq_track_centroid", "fsq_track_greedy", "fsq_track_greedy_scratch_bytes",
             "fsq_fma_peak"]
 
@@ -69,6 +69,9 @@ def load():
     L.fsq_gaussfit_batch.restype = i32
     L.fsq_gaussfit_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, _c.POINTER(LmOpts),
                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fsq_gaussfit_batch_ex.restype = i32
+    L.fsq_gaussfit_batch_ex.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, _c.POINTER(LmOpts),
+                                        vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fsq_gaussfit_batch_trace.restype = i32
     L.fsq_gaussfit_batch_trace.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, _c.POINTER(LmOpts),
                                            vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp]

@@ -58,15 +58,50 @@ struct LmArgs {
     double* out_fit; int32_t* out_int;
     unsigned long long* work_counter;
     double* trace; int trace_steps; long long trace_n;   // optional per-trial-step trace (debug/tests)
+    // general gaussfit surface (lmfit_kernel<G, false, true>): fixed parameters, residual weights, the circular model,
+    // the full covariance matrix -- gaussfitter.py:188-232, mpfit.py:917-948, :1361-1388
+    const uint8_t* fixed;      // [n,7] 1 = parinfo 'fixed' (mpfit.py:917-921) or NULL
+    const double* err;         // [n,P] residuals are divided by it (gaussfitter.py:218) or NULL
+    int circle;                // 1: width_y := width_x, no rotation (gaussfitter.py:104-107); parameters 5, 6 are not fitted
+    double* covar;             // [n,7,7] mpfit .covar (zero rows / columns for fixed parameters) or NULL
 };
 
 __device__ __forceinline__ int perm_get(unsigned perm, int j) { return (perm >> (4 * j)) & 15; }
 
-__device__ __forceinline__ double enorm7(const double* v) {
+__device__ __forceinline__ double enorm7(const double* v, int n = NP) {
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) s += v[j] * v[j];
+    for (int j = 0; j < NP; ++j) if (j < n) s += v[j] * v[j];
     return sqrt(s);
+}
+
+// Free-parameter bookkeeping of the general kernel: mpfit works on x = xall[ifree] (mpfit.py:943-948), so every
+// vector and matrix of the algorithm is indexed by the POSITION k < n of a free parameter; pmap holds ifree[k] in
+// nibble k.  The standard kernels (GEN = false) have n = 7 and the identity map at compile time.
+template <bool GEN>
+__device__ __forceinline__ int pidx(unsigned pmap, int k) { return GEN ? (int)((pmap >> (4 * k)) & 15u) : k; }
+
+// full parameter vector of the model from the free vector xs[0..n) and the fixed values pbase
+template <bool GEN>
+__device__ __forceinline__ void expand_params(const double* xs, int n, unsigned pmap, const double (&pbase)[NP], bool circle,
+                                              double (&p)[NP]) {
+    if (!GEN) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) p[j] = xs[j];
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) p[j] = pbase[j];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        if (k < n) {
+            const double v = xs[k];
+            const int pj = pidx<true>(pmap, k);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) if (pj == j) p[j] = v;
+        }
+    }
+    if (circle) p[5] = p[4];                               // gaussfitter.py:105 width_x = width_y
 }
 
 template <int S>
@@ -132,8 +167,7 @@ __device__ __forceinline__ int load_as_int(const void* base, int dtype, size_t o
 // (x, original order), st.sdiag; st.r modified in place.  faithful: the diagonal is not
 // restored and the solution is scattered into it (numpy.diagonal view, :1915/:1956/:1977).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void qrsolv(FitShared& st, unsigned perm, bool faithful) {
-    const int n = NP;
+__device__ __noinline__ void qrsolv(FitShared& st, unsigned perm, bool faithful, const int n) {
     for (int j = 0; j < n; ++j)
         for (int i = j; i < n; ++i) st.r[i][j] = st.r[j][i];
     if (!faithful)
@@ -193,8 +227,7 @@ __device__ __noinline__ void qrsolv(FitShared& st, unsigned perm, bool faithful)
 // lmpar -- mpfit.py:2077-2190.  Returns the new par; step (un-negated) in st.step.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta, double par,
-                                     bool faithful, int& n_qrsolv) {
-    const int n = NP;
+                                     bool faithful, int& n_qrsolv, const int n) {
     double dmax = 0.0;
     for (int j = 0; j < n; ++j) dmax = fmax(dmax, fabs(st.r[j][j]));
     const double rthresh = dmax * FSQ_MACHEP;
@@ -210,7 +243,7 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
     }
     for (int j = 0; j < n; ++j) st.step[perm_get(perm, j)] = st.lw1[j];
     for (int j = 0; j < n; ++j) st.lw2[j] = st.diag[j] * st.step[j];
-    double dxnorm = enorm7(st.lw2);
+    double dxnorm = enorm7(st.lw2, n);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) return 0.0;                       // Gauss-Newton step accepted (:2112)
 
@@ -223,7 +256,7 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
             for (int i = 0; i < j; ++i) sum0 += st.r[i][j] * st.lw1[i];
             st.lw1[j] = (st.lw1[j] - sum0) / st.r[j][j];
         }
-        const double temp = enorm7(st.lw1);
+        const double temp = enorm7(st.lw1, n);
         parl = ((fp / delta) / temp) / temp;
     }
     for (int j = 0; j < n; ++j) {
@@ -231,7 +264,7 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
         for (int i = 0; i <= j; ++i) sum0 += st.r[i][j] * st.qtf[i];
         st.lw1[j] = sum0 / st.diag[perm_get(perm, j)];
     }
-    const double gnorm = enorm7(st.lw1);
+    const double gnorm = enorm7(st.lw1, n);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = FSQ_DWARF / fmin(delta, 0.1);
     par = fmax(par, parl);
@@ -245,9 +278,9 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
         double temp = sqrt(par);
         for (int j = 0; j < n; ++j) st.lw1[j] = temp * st.diag[j];
         ++n_qrsolv;
-        qrsolv(st, perm, faithful);
+        qrsolv(st, perm, faithful, n);
         for (int j = 0; j < n; ++j) st.lw2[j] = st.diag[j] * st.step[j];
-        dxnorm = enorm7(st.lw2);
+        dxnorm = enorm7(st.lw2, n);
         temp = fp;
         fp = dxnorm - delta;
         if ((fabs(fp) <= 0.1 * delta) || ((parl == 0.0) && (fp <= temp) && (temp < 0.0)) || (iter == 10)) break;
@@ -258,7 +291,7 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
             for (int i = j + 1; i < n; ++i) st.lw1[i] = st.lw1[i] - st.r[i][j] * t;
         }
         st.lw1[n - 1] = st.lw1[n - 1] / st.sdiag[n - 1];
-        temp = enorm7(st.lw1);
+        temp = enorm7(st.lw1, n);
         const double parc = ((fp / delta) / temp) / temp;
         if (fp > 0.0) parl = fmax(parl, par);
         if (fp < 0.0) paru = fmin(paru, par);
@@ -270,8 +303,7 @@ __device__ __noinline__ double lmpar(FitShared& st, unsigned perm, double delta,
 // ------------------------------------------------------------------------------------------
 // covariance -> perror (mpfit.py:2274-2336, :1361-1388).  Works in st.r (destroyed).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void covar_perror(FitShared& st, unsigned perm, double* perr /*st.lw1*/) {
-    const int n = NP;
+__device__ __noinline__ void covar_perror(FitShared& st, unsigned perm, double* perr /*st.lw1*/, const int n) {
     double (*r)[NP] = st.r;
     int l = -1;
     const double tolr = 1.e-14 * fabs(r[0][0]);
@@ -295,18 +327,37 @@ __device__ __noinline__ void covar_perror(FitShared& st, unsigned perm, double* 
             for (int i = 0; i <= k; ++i) r[i][k] = temp * r[i][k];
         }
     }
-    // only the diagonal of the un-pivoted covariance is needed for perror: wa[jj] = r[j][j]
+    // the full lower triangle of the covariance in the strict lower triangle of r and in wa (mpfit.py:2313-2327);
+    // wa = st.lw2.  (Position (ii, jj) with ii > jj is only ever written, never read, by a later (i, j) of this
+    // loop: reads are confined to i <= j, the upper triangle.)
     for (int j = 0; j < n; ++j) {
         const int jj = perm_get(perm, j);
-        const double d = (j > l) ? 0.0 : r[j][j];
-        perr[jj] = (d >= 0.0) ? sqrt(d) : 0.0;
+        const bool sing = j > l;
+        for (int i = 0; i <= j; ++i) {
+            if (sing) r[i][j] = 0.0;
+            const int ii = perm_get(perm, i);
+            if (ii > jj) r[ii][jj] = r[i][j];
+            if (ii < jj) r[jj][ii] = r[i][j];
+        }
+        st.lw2[jj] = r[j][j];
+    }
+    for (int j = 0; j < n; ++j) {                            // symmetrize (:2330-2333)
+        for (int i = 0; i <= j; ++i) r[i][j] = r[j][i];
+        r[j][j] = st.lw2[j];
+    }
+    for (int j = 0; j < n; ++j) {                            // perror = sqrt(diag) where diag >= 0 (:1382-1386)
+        const double d = r[j][j];
+        perr[j] = (d >= 0.0) ? sqrt(d) : 0.0;
     }
 }
 
 // ==========================================================================================
-template <int G, bool PFLIB>
+// GEN: the general gaussfit surface (fixed parameters, weights, circular model): n free parameters at run time.
+// GEN = false instantiations are the standard 7-parameter kernels, arithmetic unchanged.
+template <int G, bool PFLIB, bool GEN = false>
 __global__ void __launch_bounds__(LM_THREADS)
 lmfit_kernel(const LmArgs a) {
+    static_assert(!(PFLIB && GEN), "the frame path is always the 7-parameter model");
     constexpr int S = SLOTS;
     extern __shared__ __align__(16) unsigned char fsq_smem[];
     const int lane32 = threadIdx.x & 31;
@@ -336,6 +387,13 @@ lmfit_kernel(const LmArgs a) {
 
     // ---- per-fit state (registers) ----
     double dat[S], fv[S], E[S];
+    double wgt[GEN ? S : 1];                          // residual weights 1 / err (GEN)
+    double pbase[NP];                                 // full start vector: the values of the fixed parameters (GEN)
+    int n = NP;                                       // free parameters
+    unsigned pmap = 0x6543210u;                       // ifree
+    const bool circle = GEN && (a.circle != 0);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) pbase[j] = 0.0;
     int idat[S];
     Rot<S> rot;
     long long idx = 0;
@@ -424,14 +482,45 @@ lmfit_kernel(const LmArgs a) {
                     p0v = a.p0[idx * NP + g]; lov = a.lo[idx * NP + g]; hiv = a.hi[idx * NP + g];
                     ql = a.lim_lo[idx * NP + g] != 0; qu = a.lim_hi[idx * NP + g] != 0;
                 }
+                if (GEN) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const int pix = s * G + g;
+                        wgt[GEN ? s : 0] = (a.err && valid[s]) ? a.err[wbase + pix] : 1.0;
+                    }
+                }
+            }
+            bool is_fixed = false;
+            if (GEN) {
+                // free parameters (mpfit.py:917-948): parinfo 'fixed'; the circular model has no parameters 5, 6
+                is_fixed = (g < NP) && ((a.fixed && a.fixed[idx * NP + g] != 0) || (circle && g >= 5));
+                const unsigned freem = (__ballot_sync(gmask, (g < NP) && !is_fixed) >> gbase) & 0x7fu;
+                n = __popc(freem);
+                pmap = 0;
+                {
+                    int k = 0;
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) if ((freem >> j) & 1u) { pmap |= (unsigned)j << (4 * k); ++k; }
+                }
+#pragma unroll
+                for (int j = 0; j < NP; ++j) pbase[j] = __shfl_sync(gmask, p0v, j, G);
+            }
+            // mpfit.py:956-964 limit checks -> status 0, niter 0 (the start check covers fixed parameters too,
+            // the consistency check only free ones)
+            const bool bad1 = (g < NP) && ((ql && p0v < lov) || (qu && p0v > hiv));
+            const bool bad2 = (g < NP) && (ql && qu && lov >= hiv) && !is_fixed;
+            if (GEN) {
+                // compress to the free positions: lane k < n takes the values of parameter ifree[k]
+                const int src = (g < n) ? pidx<true>(pmap, g) : 0;
+                const double c_p0 = __shfl_sync(gmask, p0v, src, G), c_lo = __shfl_sync(gmask, lov, src, G),
+                             c_hi = __shfl_sync(gmask, hiv, src, G);
+                const bool c_ql = __shfl_sync(gmask, (int)ql, src, G) != 0, c_qu = __shfl_sync(gmask, (int)qu, src, G) != 0;
+                p0v = c_p0; lov = c_lo; hiv = c_hi; ql = c_ql && (g < n); qu = c_qu && (g < n);
             }
             if (g < NP) { st.x[g] = p0v; st.llim[g] = lov; st.ulim[g] = hiv; }
             qll = (__ballot_sync(gmask, ql && g < NP) >> gbase) & 0x7fu;
             qul = (__ballot_sync(gmask, qu && g < NP) >> gbase) & 0x7fu;
-            // mpfit.py:956-964 limit checks -> status 0, niter 0
-            const bool bad1 = (g < NP) && ((ql && p0v < lov) || (qu && p0v > hiv));
-            const bool bad2 = (g < NP) && (ql && qu && lov >= hiv);
-            const bool bad = __any_sync(gmask, bad1 || bad2);
+            const bool bad = __any_sync(gmask, bad1 || bad2) || (GEN && n == 0);      // 'no free parameters' (:944-946)
             __syncwarp(gmask);
             if (bad) {
                 status = 0; niter = 0; nfev = 0; fnorm = -1.0; fnorm1 = -1.0;
@@ -444,7 +533,16 @@ lmfit_kernel(const LmArgs a) {
                         a.out_int[idx * 4 + 2] = 0; a.out_int[idx * 4 + 3] = 0;
                     }
                 } else {
-                    if (g < NP) { a.params[idx * NP + g] = p0v; if (a.perror) a.perror[idx * NP + g] = 0.0; }
+                    if (g < NP) {
+                        double pv = p0v;
+                        if (GEN) {
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) if (g == j) pv = pbase[j];
+                        }
+                        a.params[idx * NP + g] = pv;
+                        if (a.perror) a.perror[idx * NP + g] = 0.0;
+                    }
+                    if (GEN && a.covar) for (int q = g; q < NP * NP; q += G) a.covar[idx * NP * NP + q] = 0.0;
                     if (g == 0) {
                         a.status[idx] = 0; a.niter[idx] = 0; a.nfev[idx] = 0; a.chi2[idx] = -1.0;
                         if (a.n_qrsolv) a.n_qrsolv[idx] = 0;
@@ -456,14 +554,14 @@ lmfit_kernel(const LmArgs a) {
             // first residual (mpfit.py:999), fnorm (:1019)
             {
                 double p[NP];
-#pragma unroll
-                for (int j = 0; j < NP; ++j) p[j] = st.x[j];
+                expand_params<GEN>(st.x, n, pmap, pbase, circle, p);
                 make_rot<S>(p[6], px, py, rot);
                 eval_E<S>(p, rot, E);
                 double ss = 0.0;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     fv[s] = valid[s] ? __dsub_rn(dat[s], model_of(p[0], p[1], E[s])) : 0.0;
+                    if (GEN) fv[s] = __ddiv_rn(fv[s], wgt[GEN ? s : 0]);                 // gaussfitter.py:218
                     ss = fma(fv[s], fv[s], ss);
                 }
                 fnorm = sqrt(group_sum<G>(ss, gmask));
@@ -474,24 +572,32 @@ lmfit_kernel(const LmArgs a) {
         // ================================================================ jacobian phase
         if (need_jac) {
             double J[S][NP];
-            double p[NP];
+            double p[NP];                                  // full parameter vector of the model
+            double xc[NP];                                 // free vector x = xall[ifree] (== p when !GEN)
 #pragma unroll
-            for (int j = 0; j < NP; ++j) p[j] = st.x[j];
+            for (int j = 0; j < NP; ++j) xc[j] = st.x[j];
+            expand_params<GEN>(st.x, n, pmap, pbase, circle, p);
             // ---- forward differences, mpfit.py:1512-1612 ----
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                const double xj = p[j];
+                if (GEN && j >= n) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) J[s][j] = 0.0;             // no such column: inert in everything below
+                    continue;
+                }
+                const int pj = pidx<GEN>(pmap, j);         // which model parameter position j perturbs
+                const double xj = xc[j];
                 double h = FSQ_SQRT_MACHEP * fabs(xj);
                 if (h == 0.0) h = FSQ_SQRT_MACHEP;
                 if (((qul >> j) & 1u) && (xj > st.ulim[j] - h)) h = -h;
                 const double xph = xj + h;
                 double Ep[S];
-                if (j >= 2) {
+                if (pj >= 2) {
                     double q[NP];
 #pragma unroll
-                    for (int i = 0; i < NP; ++i) q[i] = p[i];
-                    q[j] = xph;
-                    if (j == 6) {
+                    for (int i = 0; i < NP; ++i) q[i] = (GEN ? (pj == i) : (j == i)) ? xph : p[i];
+                    if (GEN && circle) q[5] = q[4];
+                    if (pj == 6) {
                         Rot<S> r2;
                         make_rot<S>(xph, px, py, r2);
                         eval_E<S>(q, r2, Ep);
@@ -502,20 +608,21 @@ lmfit_kernel(const LmArgs a) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     double gm;
-                    if (j == 0) gm = model_of(xph, p[1], E[s]);
-                    else if (j == 1) gm = model_of(p[0], xph, E[s]);
+                    if (pj == 0) gm = model_of(xph, p[1], E[s]);
+                    else if (pj == 1) gm = model_of(p[0], xph, E[s]);
                     else gm = model_of(p[0], p[1], Ep[s]);
-                    const double fp_ = valid[s] ? __dsub_rn(dat[s], gm) : 0.0;
+                    double fp_ = valid[s] ? __dsub_rn(dat[s], gm) : 0.0;
+                    if (GEN) fp_ = __ddiv_rn(fp_, wgt[GEN ? s : 0]);
                     J[s][j] = __ddiv_rn(__dsub_rn(fp_, fv[s]), h);              // mpfit.py:1599
                 }
             }
-            nfev += NP;
+            nfev += n;
             // ---- pegged parameters, mpfit.py:1073-1091 ----
             lpeg = 0; upeg = 0;
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                const bool lp = ((qll >> j) & 1u) && (p[j] == st.llim[j]);
-                const bool up = ((qul >> j) & 1u) && (p[j] == st.ulim[j]);
+                const bool lp = ((qll >> j) & 1u) && (xc[j] == st.llim[j]);
+                const bool up = ((qul >> j) & 1u) && (xc[j] == st.ulim[j]);
                 if (lp || up) {
                     double d = 0.0;
 #pragma unroll
@@ -548,9 +655,9 @@ lmfit_kernel(const LmArgs a) {
             bool qr_active = true;
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-                if (qr_active) {
+                if (qr_active && (!GEN || j < n)) {
                     // pivot: first position with the largest remaining norm
-                    const double cand = (g >= j && g < NP) ? rdiag_l : -1.0;
+                    const double cand = (g >= j && g < n) ? rdiag_l : -1.0;
                     double rmax = cand;
 #pragma unroll
                     for (int m = G / 2; m >= 1; m >>= 1) rmax = fmax(rmax, __shfl_xor_sync(gmask, rmax, m, G));
@@ -609,7 +716,7 @@ lmfit_kernel(const LmArgs a) {
                                 if (g == k) ajk_l = v;
                             }
                             bool redo = false;
-                            if (g > j && g < NP && rdiag_l != 0.0) {
+                            if (g > j && g < n && rdiag_l != 0.0) {
                                 double temp = ajk_l / rdiag_l;
                                 rdiag_l = rdiag_l * sqrt(fmax(1.0 - temp * temp, 0.0));
                                 temp = rdiag_l / wa_l;
@@ -664,7 +771,7 @@ lmfit_kernel(const LmArgs a) {
             // ---- first-iteration scaling, mpfit.py:1099-1110 ----
             if (niter == 1) {
                 double ss = 0.0;
-                for (int j = 0; j < NP; ++j) {
+                for (int j = 0; j < n; ++j) {
                     double d = st.acnorm[j];
                     if (d == 0.0) d = 1.0;
                     st.diag[j] = d;
@@ -678,7 +785,7 @@ lmfit_kernel(const LmArgs a) {
             // ---- scaled gradient norm, mpfit.py:1142-1148 ----
             gnorm = 0.0;
             if (fnorm != 0.0) {
-                for (int j = 0; j < NP; ++j) {
+                for (int j = 0; j < n; ++j) {
                     const int l = perm_get(perm, j);
                     const double an = st.acnorm[l];
                     if (an != 0.0) {
@@ -692,7 +799,7 @@ lmfit_kernel(const LmArgs a) {
             if (gnorm <= gtol) status = 4;                      // :1151
             else if (maxiter == 0) status = 5;                  // :1154
             else {
-                for (int j = 0; j < NP; ++j) st.diag[j] = (st.diag[j] > st.acnorm[j]) ? st.diag[j] : st.acnorm[j];  // :1160
+                for (int j = 0; j < n; ++j) st.diag[j] = (st.diag[j] > st.acnorm[j]) ? st.diag[j] : st.acnorm[j];  // :1160
             }
             need_jac = false;
             __syncwarp(gmask);
@@ -700,24 +807,24 @@ lmfit_kernel(const LmArgs a) {
 
         // ================================================================ trial phase
         if (status == 0) {
-            par = lmpar(st, perm, delta, par, faithful, n_qrsolv);          // :1167
+            par = lmpar(st, perm, delta, par, faithful, n_qrsolv, n);       // :1167
             __syncwarp(gmask);
             double alpha = 1.0;
-            for (int j = 0; j < NP; ++j) st.step[j] = -st.step[j];          // :1170
+            for (int j = 0; j < n; ++j) st.step[j] = -st.step[j];           // :1170
             if (qll | qul) {                                                // :1184-1202
                 if (lpeg) {
                     double mx = st.step[0];
-                    for (int j = 1; j < NP; ++j) mx = fmax(mx, st.step[j]);
-                    for (int j = 0; j < NP; ++j)
+                    for (int j = 1; j < n; ++j) mx = fmax(mx, st.step[j]);
+                    for (int j = 0; j < n; ++j)
                         if ((lpeg >> j) & 1u) st.step[j] = fmin(fmax(st.step[j], 0.0), mx);
                 }
                 if (upeg) {
                     double mn = st.step[0];
-                    for (int j = 1; j < NP; ++j) mn = fmin(mn, st.step[j]);
-                    for (int j = 0; j < NP; ++j)
+                    for (int j = 1; j < n; ++j) mn = fmin(mn, st.step[j]);
+                    for (int j = 0; j < n; ++j)
                         if ((upeg >> j) & 1u) st.step[j] = fmin(fmax(st.step[j], mn), 0.0);
                 }
-                for (int j = 0; j < NP; ++j) {
+                for (int j = 0; j < n; ++j) {
                     const double sj = st.step[j], xj = st.x[j];
                     if (fabs(sj) > FSQ_MACHEP) {
                         if (((qll >> j) & 1u) && (xj + sj < st.llim[j])) alpha = fmin(alpha, (st.llim[j] - xj) / sj);
@@ -727,7 +834,7 @@ lmfit_kernel(const LmArgs a) {
             }
             double pn = 0.0;
             bool nonfinite = false;
-            for (int j = 0; j < NP; ++j) {                                  // :1215-1234
+            for (int j = 0; j < n; ++j) {                                   // :1215-1234
                 const double sj = st.step[j] * alpha;
                 st.step[j] = sj;
                 double xn = st.x[j] + sj;
@@ -751,15 +858,18 @@ lmfit_kernel(const LmArgs a) {
             double f1[S], E1[S];
             Rot<S> rot1;
             double pt[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) pt[j] = st.xnew[j];
-            if (pt[6] == st.x[6]) rot1 = rot; else make_rot<S>(pt[6], px, py, rot1);
+            expand_params<GEN>(st.xnew, n, pmap, pbase, circle, pt);
+            bool same_rot;
+            if (GEN) { double pc[NP]; expand_params<GEN>(st.x, n, pmap, pbase, circle, pc); same_rot = pt[6] == pc[6]; }
+            else same_rot = pt[6] == st.x[6];
+            if (same_rot) rot1 = rot; else make_rot<S>(pt[6], px, py, rot1);
             eval_E<S>(pt, rot1, E1);
             {
                 double ss = 0.0;
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     f1[s] = valid[s] ? __dsub_rn(dat[s], model_of(pt[0], pt[1], E1[s])) : 0.0;
+                    if (GEN) f1[s] = __ddiv_rn(f1[s], wgt[GEN ? s : 0]);
                     ss = fma(f1[s], f1[s], ss);
                 }
                 fnorm1 = sqrt(group_sum<G>(ss, gmask));
@@ -768,13 +878,13 @@ lmfit_kernel(const LmArgs a) {
             // ---- actual / predicted reduction, mpfit.py:1253-1273 ----
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = -(q * q) + 1.0; }
-            for (int j = 0; j < NP; ++j) st.lw2[j] = 0.0;
-            for (int j = 0; j < NP; ++j) {
+            for (int j = 0; j < n; ++j) st.lw2[j] = 0.0;
+            for (int j = 0; j < n; ++j) {
                 const double sj = st.step[perm_get(perm, j)];
                 for (int i = 0; i <= j; ++i) st.lw2[i] = st.lw2[i] + st.r[i][j] * sj;
             }
             double t1 = 0.0;
-            for (int j = 0; j < NP; ++j) { const double t = alpha * st.lw2[j]; t1 += t * t; }
+            for (int j = 0; j < n; ++j) { const double t = alpha * st.lw2[j]; t1 += t * t; }
             const double temp1 = sqrt(t1) / fnorm;
             const double temp2 = (sqrt(alpha * par) * pnorm) / fnorm;
             const double prered = temp1 * temp1 + (temp2 * temp2) / 0.5;
@@ -796,7 +906,7 @@ lmfit_kernel(const LmArgs a) {
             const bool accepted = ratio >= 0.0001;                          // :1291-1298
             if (accepted) {
                 double ss = 0.0;
-                for (int j = 0; j < NP; ++j) {
+                for (int j = 0; j < n; ++j) {
                     const double xn = st.xnew[j];
                     st.x[j] = xn;
                     const double t = st.diag[j] * xn;
@@ -825,7 +935,7 @@ lmfit_kernel(const LmArgs a) {
                 else if (nonfinite || !isfinite(ratio)) status = -16;       // :1330-1335
             }
             if (a.trace && idx < a.trace_n && g == 0) {
-                const int stepno = nfev - 2 - NP * (niter - (accepted ? 1 : 0));   // trial index (0-based)
+                const int stepno = nfev - 2 - n * (niter - (accepted ? 1 : 0));    // trial index (0-based)
                 const int slot = nfev;   // unique, increasing
                 (void)stepno;
                 double* tr = a.trace + ((size_t)idx * a.trace_steps) * 20;
@@ -849,14 +959,14 @@ lmfit_kernel(const LmArgs a) {
             const double fn = fmax(fnorm, fnorm1);                          // :1357-1359
             const double chi2 = fn * fn;
             double pf[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) pf[j] = st.x[j];
+            expand_params<GEN>(st.x, n, pmap, pbase, circle, pf);
             double gimg[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) gimg[s] = model_of(pf[0], pf[1], E[s]);   // gaussfitter.py:253
-            const bool want_pe = (a.o.want_perror != 0) && (PFLIB ? false : (a.perror != nullptr));
+            const bool want_cv = !PFLIB && (a.covar != nullptr);
+            const bool want_pe = ((a.o.want_perror != 0) && (PFLIB ? false : (a.perror != nullptr))) || want_cv;
             if (want_pe) {
-                if (status > 0) covar_perror(st, perm, st.lw1);
+                if (status > 0) covar_perror(st, perm, st.lw1, n);
                 else for (int j = 0; j < NP; ++j) st.lw1[j] = __longlong_as_double(0x7ff8000000000000LL);   // perror is None there
                 __syncwarp(gmask);
             }
@@ -903,9 +1013,30 @@ lmfit_kernel(const LmArgs a) {
                     for (int s = 0; s < S; ++s) if (valid[s]) a.fit_img[idx * 25 + s * G + g] = gimg[s];
                 }
             } else {
-                if (g < NP) {
-                    a.params[idx * NP + g] = st.x[g];
-                    if (a.perror) a.perror[idx * NP + g] = want_pe ? st.lw1[g] : 0.0;
+                if (!GEN) {
+                    if (g < NP) {
+                        a.params[idx * NP + g] = st.x[g];
+                        if (a.perror) a.perror[idx * NP + g] = want_pe ? st.lw1[g] : 0.0;
+                    }
+                } else if (g == 0) {
+                    // mpfit.py:1346-1348, :1375-1386: full-length vectors, zeros where a parameter is fixed
+                    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) a.params[idx * NP + j] = pf[j];
+                    if (a.perror) {
+                        for (int j = 0; j < NP; ++j) a.perror[idx * NP + j] = (want_pe && status <= 0) ? nanv : 0.0;
+                        if (want_pe && status > 0)
+                            for (int k = 0; k < n; ++k) a.perror[idx * NP + pidx<true>(pmap, k)] = st.lw1[k];
+                    }
+                }
+                if (want_cv && g == 0) {
+                    // mpfit.py:1375-1379: covar[ifree, ifree[i]] = cv[:, i]; None (NaN here) when the fit did not converge
+                    double* cv = a.covar + idx * NP * NP;
+                    const double fill = (status > 0) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
+                    for (int q = 0; q < NP * NP; ++q) cv[q] = fill;
+                    if (status > 0)
+                        for (int i = 0; i < n; ++i)
+                            for (int k = 0; k < n; ++k) cv[pidx<GEN>(pmap, i) * NP + pidx<GEN>(pmap, k)] = st.r[i][k];
                 }
                 if (g == 0) {
                     a.status[idx] = status; a.niter[idx] = niter; a.nfev[idx] = nfev; a.chi2[idx] = chi2;
@@ -929,12 +1060,15 @@ static int launch_lm(const LmArgs& a, int G, bool pflib, cudaStream_t st) {
     int blocks_per_sm = 4;
     const int grid = sm_count() * blocks_per_sm;
     FSQ_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+    const bool gen = (a.fixed != nullptr) || (a.err != nullptr) || (a.circle != 0);
     if (pflib) {
         lmfit_kernel<8, true><<<grid, LM_THREADS, smem, st>>>(a);
     } else if (G == 8) {
-        lmfit_kernel<8, false><<<grid, LM_THREADS, smem, st>>>(a);
+        if (gen) lmfit_kernel<8, false, true><<<grid, LM_THREADS, smem, st>>>(a);
+        else lmfit_kernel<8, false><<<grid, LM_THREADS, smem, st>>>(a);
     } else {
-        lmfit_kernel<32, false><<<grid, LM_THREADS, smem, st>>>(a);
+        if (gen) lmfit_kernel<32, false, true><<<grid, LM_THREADS, smem, st>>>(a);
+        else lmfit_kernel<32, false><<<grid, LM_THREADS, smem, st>>>(a);
     }
     FSQ_LAUNCH_CHECK();
     return FSQ_OK;
@@ -991,6 +1125,17 @@ extern "C" int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n
                                   double* params, double* perror, int32_t* status, int32_t* niter,
                                   int32_t* nfev, double* chi2, int32_t* n_qrsolv, double* fit_img,
                                   int64_t* work_counter, void* stream) {
+    return fsq_gaussfit_batch_ex(windows, dtype_code, n, win, p0, lo, hi, lim_lo, lim_hi, nullptr, nullptr, 0, opts, params,
+                                 perror, nullptr, status, niter, nfev, chi2, n_qrsolv, fit_img, work_counter, stream);
+}
+
+extern "C" int fsq_gaussfit_batch_ex(const void* windows, int dtype_code, int64_t n, int win,
+                                     const double* p0, const double* lo, const double* hi,
+                                     const uint8_t* lim_lo, const uint8_t* lim_hi, const uint8_t* fixed,
+                                     const double* err, int circle, const fsq_lm_opts* opts,
+                                     double* params, double* perror, double* covar, int32_t* status, int32_t* niter,
+                                     int32_t* nfev, double* chi2, int32_t* n_qrsolv, double* fit_img,
+                                     int64_t* work_counter, void* stream) {
     int rc = check_opts(opts, "fsq_gaussfit_batch");
     if (rc) return rc;
     if (n < 0) { set_error("fsq_gaussfit_batch: n < 0"); return FSQ_E_ARG; }
@@ -1009,6 +1154,11 @@ extern "C" int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n
         return FSQ_E_ARG;
     }
     if (opts->want_perror && !perror) { set_error("fsq_gaussfit_batch: want_perror set but perror is NULL"); return FSQ_E_ARG; }
+    if ((fixed || err || circle || covar) && opts->solver != FSQ_SOLVER_MINPACK) {
+        set_error("fsq_gaussfit_batch_ex: fixed parameters, err weights, the circular model and covar need FSQ_SOLVER_MINPACK");
+        return FSQ_E_ARG;
+    }
+    if (win * win < 7) { set_error("fsq_gaussfit_batch: number of parameters must not exceed data"); return FSQ_E_ARG; }
     if (opts->solver == FSQ_SOLVER_FAST) {
         if (win != 5 && win != 11) { set_error("fsq_gaussfit_batch: FSQ_SOLVER_FAST takes 5x5 or 11x11 windows (got %d); use FSQ_SOLVER_MINPACK", win); return FSQ_E_ARG; }
         if (opts->want_perror) { set_error("fsq_gaussfit_batch: want_perror needs FSQ_SOLVER_MINPACK"); return FSQ_E_ARG; }
@@ -1028,6 +1178,7 @@ extern "C" int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n
     a.n = n; a.n_dev = nullptr; a.o = *opts;
     a.params = params; a.perror = perror; a.status = status; a.niter = niter; a.nfev = nfev;
     a.chi2 = chi2; a.n_qrsolv = n_qrsolv; a.fit_img = fit_img;
+    a.fixed = fixed; a.err = err; a.circle = circle ? 1 : 0; a.covar = covar;
     a.work_counter = (unsigned long long*)work_counter;
     const int G = (win * win <= 8 * SLOTS) ? 8 : 32;
     return launch_lm(a, G, false, (cudaStream_t)stream);

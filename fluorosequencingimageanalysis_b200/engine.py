@@ -184,12 +184,17 @@ def fit_candidates(frames, cand_hw, cand_frame, n, faithful=True, want_fit_img=F
 
 
 class FitBatch(object):
-    __slots__ = ("params", "perror", "status", "niter", "nfev", "chi2", "n_qrsolv", "fit_img")
+    __slots__ = ("params", "perror", "covar", "status", "niter", "nfev", "chi2", "n_qrsolv", "fit_img")
 
 
 def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perror=False,
-                   want_fit_img=False, opts=None, solver="minpack", rescue=None, **mpfit_kw):
+                   want_fit_img=False, opts=None, solver="minpack", rescue=None, fixed=None, err=None,
+                   circle=False, want_covar=False, **mpfit_kw):
     """gaussfitter.gaussfit -> mpfit (agpy/gaussfitter.py:142-255) for n windows [n,win,win].
+
+    ``fixed`` [n,7] (parinfo 'fixed'), ``err`` [n,win,win] (residual weights), ``circle`` (the circular model) and
+    ``want_covar`` (mpfit .covar -> FitBatch.covar [n,7,7]) are the rest of gaussfit's surface
+    (fsq_gaussfit_batch_ex, MINPACK solver only); parameters keep the 7-slot layout.
 
     ``rescue`` (default: on for solver="fast"): the FAST solver keeps its normal equations in FP32 and reports
     status -16 when they leave the finite range (measured: 0.03 % of 11x11 windows cut from a dense field, fits
@@ -233,11 +238,15 @@ def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perr
     r.chi2 = torch.empty(n, dtype=torch.float64, device=dev)
     r.n_qrsolv = torch.empty(n, dtype=torch.int32, device=dev)
     r.fit_img = torch.empty((n, win, win), dtype=torch.float64, device=dev) if want_fit_img else None
+    r.covar = torch.empty((n, 7, 7), dtype=torch.float64, device=dev) if want_covar else None
+    fixed_d = dv(fixed, torch.uint8).reshape(n, 7) if fixed is not None else None
+    err_d = dv(err, torch.float64).reshape(n, win, win) if err is not None else None
     counter = torch.zeros(1, dtype=torch.int64, device=dev)
-    rc = L.fsq_gaussfit_batch(_ptr(w), _TORCH_DTYPE_CODE[w.dtype], n, win, _ptr(p0), _ptr(lo), _ptr(hi),
-                              _ptr(lim_lo), _ptr(lim_hi), ctypes.byref(o), _ptr(r.params), _ptr(r.perror),
-                              _ptr(r.status), _ptr(r.niter), _ptr(r.nfev), _ptr(r.chi2), _ptr(r.n_qrsolv),
-                              _ptr(r.fit_img), _ptr(counter), _stream())
+    rc = L.fsq_gaussfit_batch_ex(_ptr(w), _TORCH_DTYPE_CODE[w.dtype], n, win, _ptr(p0), _ptr(lo), _ptr(hi),
+                                 _ptr(lim_lo), _ptr(lim_hi), _ptr(fixed_d), _ptr(err_d), 1 if circle else 0,
+                                 ctypes.byref(o), _ptr(r.params), _ptr(r.perror), _ptr(r.covar),
+                                 _ptr(r.status), _ptr(r.niter), _ptr(r.nfev), _ptr(r.chi2), _ptr(r.n_qrsolv),
+                                 _ptr(r.fit_img), _ptr(counter), _stream())
     _lib.check(rc)
     if rescue is None:
         rescue = (solver == "fast" and opts is None)

@@ -4,8 +4,9 @@ Drop-in mirror of the reference's ``gaussfitter`` 2-D entry points (agpy/gaussfi
 itself (the ``mpfit`` call of gaussfitter.py:243) runs in the CUDA LM kernel of libfsq.so.
 
 What cannot be dropped in: ``mpfit`` with an arbitrary Python
-callable.  The GPU path covers what this code base uses: the 7-parameter model
-(circle=0, rotate=1, vheight=1), err=None, no fixed parameters.
+callable.  The GPU path covers every form of ``gaussfit``: the 7-parameter model and its reduced
+forms (``circle``, ``rotate=0``, ``vheight=0``), ``fixed`` parameters, ``err`` weights, and the
+``perror`` / ``covar`` of the mpfit object (fsq_gaussfit_batch_ex).
 """
 import numpy as np
 from numpy import pi
@@ -77,10 +78,10 @@ class MpfitResult(object):
                -16: "ERROR: parameter or function value(s) have become infinite; "
                     "check model function for over- and underflow"}
 
-    def __init__(self, params, perror, status, niter, nfev, fnorm, dof, n_qrsolv):
+    def __init__(self, params, perror, status, niter, nfev, fnorm, dof, n_qrsolv, covar=None):
         self.params = params
         self.perror = perror
-        self.covar = None            # not produced by the batched kernel (perror is)
+        self.covar = covar           # mpfit.py:1361-1388 (None unless the fit converged)
         self.status = status
         self.niter = niter
         self.nfev = nfev
@@ -113,34 +114,64 @@ def gaussfit(data, err=None, params=(), autoderiv=True, return_all=False, circle
         params[usemoment] = moment[usemoment]
     elif len(params) == 0:
         params = np.array(moments(data, circle, rotate, vheight, **kwargs), dtype='float')
-    if circle or not rotate or not vheight or err is not None or np.any(np.asarray(fixed)):
-        raise NotImplementedError("the CUDA path fits the 7-parameter model (circle=0, rotate=1, "
-                                  "vheight=1, err=None, no fixed parameters) -- SURVEY.md 8(b)")
-    if len(params) != 7:
-        raise ValueError("expected 7 parameters, got %d" % len(params))
-    lmin = np.asarray(limitedmin, dtype=bool)
-    lmax = np.asarray(limitedmax, dtype=bool)
-    mn = np.asarray(minpars, dtype=float)
-    mx = np.asarray(maxpars, dtype=float)
+    # ---- the parameter layouts of gaussfitter.py:195-232, mapped onto the kernel's 7 slots
+    #      (height, amplitude, p2, p3, width_x, width_y, rota):
+    #   vheight=0: a 0 is put in front and fixed[0] is set -- in the caller's array when the default is used, like the
+    #              reference's mutable default (gaussfitter.py:195-198)
+    #   circle=1 : parinfo has no entries 5 / 6 (:224-232), the model ties width_y to width_x (:104-107)
+    #   rotate=0 : parinfo has no entry 6; rota = 0 makes the rotated model the unrotated one bit for bit
+    params = np.array(params, dtype='float')
+    if vheight == 0:
+        vheight = 1
+        params = np.concatenate([[0], params])
+        fixed[0] = 1
+    n_par = 5 if circle else (7 if rotate == 1 else 6)
+    if len(params) < n_par:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (len(params), len(params)))   # parinfo, :224-232
+    lmin = np.zeros(7, dtype=bool)
+    lmax = np.zeros(7, dtype=bool)
+    mn = np.zeros(7)
+    mx = np.zeros(7)
+    fx = np.zeros(7, dtype=np.uint8)
     for i in range(len(params)):                                             # gaussfitter.py:202-204
-        if params[i] > mx[i] and lmax[i]:
-            params[i] = mx[i]
-        if params[i] < mn[i] and lmin[i]:
-            params[i] = mn[i]
+        if params[i] > maxpars[i] and limitedmax[i]:
+            params[i] = maxpars[i]
+        if params[i] < minpars[i] and limitedmin[i]:
+            params[i] = minpars[i]
+    p7 = np.zeros(7)
+    for i in range(n_par):
+        p7[i] = params[i]
+        lmin[i], lmax[i], mn[i], mx[i] = bool(limitedmin[i]), bool(limitedmax[i]), float(minpars[i]), float(maxpars[i])
+        fx[i] = 1 if fixed[i] else 0
+    if circle:
+        p7[5] = p7[4]
+    elif rotate != 1:
+        fx[6] = 1                                                            # rota stays 0
+    general = bool(circle) or bool(fx.any()) or err is not None
     win = data[None].astype(np.int64) if data.dtype.kind in "iub" else data[None].astype(np.float64)
-    # SOLVER = "fast" runs the production fitter where it applies (5x5 / 11x11 windows, no perror asked for)
-    fast_ok = SOLVER == "fast" and win.shape[1] == win.shape[2] and win.shape[1] in (5, 11) and not (return_all or returnmp)
-    r = engine.gaussfit_batch(win, params[None], mn[None], mx[None], lmin[None].astype(np.uint8),
+    err_a = None
+    if err is not None:
+        err_a = np.broadcast_to(np.asarray(err, dtype=np.float64), data.shape)[None]
+    # SOLVER = "fast" runs the production fitter where it applies (5x5 / 11x11 windows, the plain 7-parameter model,
+    # no perror / covar asked for)
+    fast_ok = (SOLVER == "fast" and win.shape[1] == win.shape[2] and win.shape[1] in (5, 11)
+               and not (return_all or returnmp) and not general)
+    want_cv = bool(returnmp)
+    r = engine.gaussfit_batch(win, p7[None], mn[None], mx[None], lmin[None].astype(np.uint8),
                               lmax[None].astype(np.uint8), faithful=FAITHFUL, solver="fast" if fast_ok else "minpack",
-                              want_perror=bool(return_all or returnmp), want_fit_img=bool(returnfitimage))
-    p = r.params[0].cpu().numpy()
+                              want_perror=bool(return_all or returnmp), want_fit_img=bool(returnfitimage),
+                              fixed=fx[None] if general else None, err=err_a, circle=bool(circle), want_covar=want_cv)
+    p = r.params[0].cpu().numpy()[:n_par]
     status = int(r.status[0].item())
-    perror = None
+    perror = covar = None
     if r.perror is not None and status > 0:
-        perror = r.perror[0].cpu().numpy()
+        perror = r.perror[0].cpu().numpy()[:n_par]
+    if r.covar is not None and status > 0:
+        covar = r.covar[0].cpu().numpy()[:n_par, :n_par]
     if returnmp:
+        n_free = n_par - int(fx[:n_par].sum())
         returns = MpfitResult(p, perror, status, int(r.niter[0].item()), int(r.nfev[0].item()),
-                              float(r.chi2[0].item()), data.size - 7, int(r.n_qrsolv[0].item()))
+                              float(r.chi2[0].item()), data.size - n_free, int(r.n_qrsolv[0].item()), covar)
     elif return_all == 0:
         returns = p
     else:

@@ -155,6 +155,26 @@ int fsq_gaussfit_batch(const void* windows, int dtype_code, int64_t n, int win,
                        int32_t* nfev, double* chi2, int32_t* n_qrsolv, double* fit_img,
                        int64_t* work_counter, void* stream);
 
+/* The rest of gaussfit's surface (agpy/gaussfitter.py:188-232) and mpfit's .covar (agpy/mpfit/mpfit.py:1361-1388,
+ * 2274-2336); FSQ_SOLVER_MINPACK only.  Every extra argument may be NULL / 0, which gives fsq_gaussfit_batch.
+ *  fixed   [n, 7] uint8   parinfo 'fixed' (mpfit.py:917-921): the parameter keeps its start value, the algorithm runs on
+ *                         the free ones only (x = xall[ifree], mpfit.py:943-948).  gaussfit's vheight = 0 is "height
+ *                         fixed at 0" (gaussfitter.py:195-198), rotate = 0 is "rota fixed at 0" (cos 0 = 1, sin 0 = 0
+ *                         exactly, so the rotated model equals the unrotated one bit for bit)
+ *  err     [n, win, win]  float64: residuals are (data - model) / err (gaussfitter.py:218)
+ *  circle  1 = the circular model (gaussfitter.py:104-107): width_y := width_x, no rotation; parameters 5 and 6 are not
+ *          fitted and come back as (width, 0); params / perror / covar keep the 7-slot layout
+ *  covar   out [n, 7, 7]  mpfit .covar: (R^T R)^-1 un-pivoted with zero rows / columns for fixed parameters; NaN when
+ *          the fit ended with status <= 0 (the reference leaves None there)
+ * perror is zero for fixed parameters (mpfit.py:1382-1386). */
+int fsq_gaussfit_batch_ex(const void* windows, int dtype_code, int64_t n, int win,
+                          const double* p0, const double* lo, const double* hi,
+                          const uint8_t* lim_lo, const uint8_t* lim_hi, const uint8_t* fixed,
+                          const double* err, int circle, const fsq_lm_opts* opts,
+                          double* params, double* perror, double* covar, int32_t* status, int32_t* niter,
+                          int32_t* nfev, double* chi2, int32_t* n_qrsolv, double* fit_img,
+                          int64_t* work_counter, void* stream);
+
 /* Same fit with a per-trial-step trace for the first trace_n windows (tests / debugging).
  * trace is [trace_n, trace_steps, 20] float64, zero-initialised by the caller; record 0 of a
  * window holds the number of records written in [0]; record k >= 1 = (niter, accepted, status,

@@ -238,6 +238,61 @@ def make_fits11(procs, name="seed0"):
         int((d["n_qrsolv"] == 0).sum())), flush=True)
 
 
+# ----------------------------------------------------------------------------- the rest of gaussfit's surface
+def variant_cases():
+    """name -> (window side, gaussfit keyword arguments as a function of the window)"""
+    F = lambda *idx: np.array([i in idx for i in range(7)])          # noqa: E731  fresh `fixed` array per call
+    pf = dict(limitedmin=[True] * 7, limitedmax=[False, False, True, True, True, True, True],
+              minpars=[0, 0, 2, 2, .75, .75, 0], maxpars=[0, 0, 3, 3, 2, 2, 360])
+    return {
+        "default11": (11, lambda w: dict(fixed=F())),
+        "circle11": (11, lambda w: dict(circle=1, fixed=F())),
+        "norotate11": (11, lambda w: dict(rotate=0, fixed=F())),
+        "noheight11": (11, lambda w: dict(vheight=0, fixed=F())),
+        "fixed_theta11": (11, lambda w: dict(fixed=F(6))),
+        "fixed_centre11": (11, lambda w: dict(fixed=F(2, 3), params=[np.median(w), w.max() - np.median(w), 5., 5., 1.5, 1.5, 0.])),
+        "err11": (11, lambda w: dict(err=np.sqrt(np.maximum(w, 1.0)), fixed=F())),
+        "circle_noheight_err11": (11, lambda w: dict(circle=1, vheight=0, err=np.sqrt(np.maximum(w, 1.0)), fixed=F())),
+        "pflib_fixed_theta5": (5, lambda w: dict(params=[np.median(w), w.max(), 2.5, 2.5, 1, 1, 0], fixed=F(6), **pf)),
+        "pflib_circle5": (5, lambda w: dict(params=[np.median(w), w.max(), 2.5, 2.5, 1], circle=1, fixed=F(), **pf)),
+    }
+
+
+def _variant_fit(args):
+    name, win = args
+    _, gaussfitter, _ = ref()
+    side, kwf = variant_cases()[name]
+    kw = kwf(win)
+    mp = gaussfitter.gaussfit(win, returnmp=True, **kw)
+    m = len(mp.params)
+    P = np.full(7, np.nan)
+    P[:m] = mp.params
+    E = np.full(7, np.nan)
+    C = np.full((7, 7), np.nan)
+    if mp.perror is not None:
+        E[:m] = mp.perror
+        C[:m, :m] = mp.covar
+    return P, E, C, mp.status, mp.niter, mp.nfev, mp.fnorm, mp.dof, m
+
+
+def make_gaussfit_variants(procs):
+    """tests/golden/gaussfit_variants.npz: the reference's own gaussfit (oracle/_ref) with circle / rotate=0 / vheight=0
+    / fixed / err on 11x11 and 5x5 windows: params, perror, covar, status, niter, nfev, fnorm, dof per window."""
+    img, cr, cc, amp = synth.synth_frame_with_truth(0)
+    w11 = synth.cut_windows(img, cr, cc, 11)[:48]
+    w5 = synth.cut_windows(img, cr, cc, 5)[:48]
+    out = {"w11": w11, "w5": w5}
+    with multiprocessing.Pool(procs) as pool:
+        for name, (side, _) in variant_cases().items():
+            wins = w11 if side == 11 else w5
+            rows = pool.map(_variant_fit, [(name, w) for w in wins], chunksize=4)
+            for i, key in enumerate(("params", "perror", "covar", "status", "niter", "nfev", "fnorm", "dof", "npar")):
+                out["%s_%s" % (name, key)] = np.array([r[i] for r in rows])
+            st, cnt = np.unique(out[name + "_status"], return_counts=True)
+            print("variant %s: status %s" % (name, dict(zip(st.tolist(), cnt.tolist()))), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "gaussfit_variants.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
@@ -252,6 +307,8 @@ if __name__ == "__main__":
         make_detect()
     if "pipeline_small" in todo:
         make_pipeline_small()
+    if "variants" in todo:
+        make_gaussfit_variants(a.procs)
     for t_ in todo:                            # fits11[:case], fits5[:case]
         kind, _, case = t_.partition(":")
         if kind == "fits11":
