@@ -367,6 +367,104 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     ss_out = ss;
 }
 
+// -------------------------------------------------------------------------------------------
+// Cooperative pass of the 11x11 kernel (COOP): the 121 pixels of a window are too many for one thread (254 registers,
+// 6 warps per SM, latency-bound: 5.6e7 fits/s) and too few for a warp, so the warp TRANSPOSES its work between the two
+// phases of a tick.  Pass: the 32 windows of the warp are processed four at a time by the four 8-lane groups -- lane gl
+// of a group takes pixels gl, gl + 8, ... of its group's window, at the trial point shuffled in from the window's owner
+// lane -- and the 28 + 7 FP32 sums and the FP64 chi^2 are reduced over the group by xor shuffles and left in the warp's
+// shared-memory accumulator rows.  Everything else of the tick (bookkeeping, Cholesky, lmpar, bounds) then runs one
+// thread per window as before, with all 32 lanes busy and no redundant work.  Pixels sit in shared memory as FP32
+// ([window][136]: groups read conflict-free), exact for integer camera data below 2^24.
+// -------------------------------------------------------------------------------------------
+constexpr int COOP_PSTR = 136;          // floats per window row of the pixel block (121 pixels, 8 (mod 32) stride)
+constexpr int COOP_ASTR = 37;           // floats per window row of the accumulator block (35 sums, odd stride)
+
+template <int WIN, bool CLAMP>
+__device__ __forceinline__ void coop_pass(const unsigned actmask, const double (&y)[WNP], const float* __restrict__ wpx,
+                                          float* __restrict__ wacc, double* __restrict__ wss, const unsigned lane) {
+    constexpr int P = WIN * WIN;
+    constexpr int SL = (P + 7) / 8;                 // pixel slots per lane
+    const unsigned grp = lane >> 3, gl = lane & 7u;
+#pragma unroll 1
+    for (int rd = 0; rd < 8; ++rd) {
+        if (((actmask >> (4 * rd)) & 0xfu) == 0u) continue;              // warp-uniform: none of the four windows is running
+        const int w = 4 * rd + (int)grp;
+        double pt[WNP];
+#pragma unroll
+        for (int j = 0; j < WNP; ++j) pt[j] = __shfl_sync(0xffffffffu, y[j], w);
+        const double Hh = pt[0], Aa = pt[1];
+        double sn, cs;
+        w_sincos_deg(pt[6], &sn, &cs);
+        const bool flat = CLAMP && ((pt[4] == 0.0) || (pt[5] == 0.0));     // see w_pass
+        const double ezero = flat ? 0.0 : 1.0;
+        const double iwx = (CLAMP && pt[4] == 0.0) ? 0.0 : 1.0 / pt[4], iwy = (CLAMP && pt[5] == 0.0) ? 0.0 : 1.0 / pt[5];
+        const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
+        // a(r, c) = (p3 - r) cxs - (p2 - c) sxs,  b(r, c) = (p3 - r) sys + (p2 - c) cys
+        const double a00 = fma(pt[3], cxs, -pt[2] * sxs), b00 = fma(pt[3], sys, pt[2] * cys);
+        const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
+        const float iwxf = (float)iwx, iwyf = (float)iwy;
+        const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
+        float A[WNT], g[WNP];
+#pragma unroll
+        for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < WNP; ++i) g[i] = 0.0f;
+        double ss = 0.0;
+        const float* px = wpx + w * COOP_PSTR + gl;
+        int r = 0, c = (int)gl;                                          // pixel gl + 8 s = (r, c), advanced by 8 per slot
+#pragma unroll 4
+        for (int sl = 0; sl < SL; ++sl) {
+            const bool ok = (sl * 8 + (int)gl) < P;
+            const double rd_ = (double)r, cd = (double)c;
+            const double av = fma(cd, sxs, fma(-rd_, cxs, a00));
+            const double bv = fma(-cd, cys, fma(-rd_, sys, b00));
+            const double E0 = w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
+            const double E = ok ? (CLAMP ? ezero * E0 : E0) : 0.0;
+            const double d = ok ? (double)px[sl * 8] : Hh;              // beyond the window: zero residual, zero Jacobian
+            const double f = d - fma(Aa, E, Hh);
+            ss = fma(f, f, ss);
+            const float af = (float)av, bf = (float)bv;
+            const float Ef = (float)E, ff = (float)f;
+            const float AE = Af * Ef;
+            const float AEa = AE * af, AEb = AE * bf;
+            float j[WNP];
+            j[1] = -Ef;
+            j[2] = AEb * cyw - AEa * sx;
+            j[3] = AEa * cxw + AEb * sy;
+            j[4] = -AEa * af * iwxf;
+            j[5] = -AEb * bf * iwyf;
+            j[6] = -AEa * bf * krot;
+            g[0] -= ff;
+#pragma unroll
+            for (int k = 1; k < WNP; ++k) {
+                g[k] = fmaf(j[k], ff, g[k]);
+                A[wtri(k, 0)] -= j[k];
+#pragma unroll
+                for (int l = 1; l <= k; ++l) A[wtri(k, l)] = fmaf(j[k], j[l], A[wtri(k, l)]);
+            }
+            c += 8;
+            if (c >= WIN) { c -= WIN; ++r; }
+        }
+        // reduce over the 8 lanes of the group (xor butterfly: identical sums in every lane), then each lane stores its share
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, m);
+#pragma unroll
+            for (int i = 1; i < WNT; ++i) A[i] += __shfl_xor_sync(0xffffffffu, A[i], m);
+#pragma unroll
+            for (int i = 0; i < WNP; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], m);
+        }
+        float* acc = wacc + w * COOP_ASTR;
+#pragma unroll
+        for (int i = 1; i < WNT; ++i) if ((unsigned)(i & 7) == gl) acc[i] = A[i];
+#pragma unroll
+        for (int i = 0; i < WNP; ++i) if ((unsigned)((WNT + i) & 7) == gl) acc[WNT + i] = g[i];
+        if (gl == 0) wss[w] = ss;
+    }
+    __syncwarp();
+}
+
 enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
 #ifndef WRECUR
 #define WRECUR 1           // forward-differenced exponentials on the pflib frame path (w_pass)
@@ -376,19 +474,26 @@ enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
 #define WLMPAR_MAX 10      // lmpar iteration limit (mpfit.py:2148)
 #endif
 
-template <int WIN, int TPB, int MINB, bool PFLIB>
+template <int WIN, int TPB, int MINB, bool PFLIB, bool COOP = false>
 __global__ void __launch_bounds__(TPB, MINB)
 lmwarp_kernel(const WarpArgs a) {
     constexpr int P = WIN * WIN;
+    static_assert(!COOP || !PFLIB, "the cooperative pass serves the generic-window entry");
     extern __shared__ __align__(16) unsigned char w_smem[];
-    double* const s_d = reinterpret_cast<double*>(w_smem);                 // [P][TPB] pixels
-    float* const s_A = reinterpret_cast<float*>(s_d + P * TPB);            // [28][TPB] column-scaled J^T J at the current point
+    // !COOP: [P][TPB] pixels (FP64) | [28][TPB] | [7][TPB];   COOP: [28][TPB] | [7][TPB] | per warp: chi^2 [32] FP64,
+    // pixel block [32][COOP_PSTR] FP32, accumulator block [32][COOP_ASTR] FP32
+    double* const s_d = reinterpret_cast<double*>(w_smem);
+    float* const s_A = COOP ? reinterpret_cast<float*>(w_smem) : reinterpret_cast<float*>(s_d + P * TPB);   // column-scaled J^T J at the current point
     float* const s_g = s_A + WNT * TPB;                                    // [7][TPB]  column-scaled J^T f
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
     double* const sd = s_d + tid;
     float* const sA = s_A + tid;
     float* const sg = s_g + tid;
+    double* const wss = reinterpret_cast<double*>(s_g + WNP * TPB) + (tid >> 5) * 32;
+    float* const wpx = reinterpret_cast<float*>(reinterpret_cast<double*>(s_g + WNP * TPB) + (TPB / 32) * 32) + (tid >> 5) * (32 * COOP_PSTR);
+    float* const wacc = reinterpret_cast<float*>(reinterpret_cast<double*>(s_g + WNP * TPB) + (TPB / 32) * 32) + (TPB / 32) * (32 * COOP_PSTR)
+                        + (tid >> 5) * (32 * COOP_ASTR);
 
     const float ftol = (float)a.o.ftol, xtol = (float)a.o.xtol, gtol = (float)a.o.gtol, factor = (float)a.o.factor;
     const float machep = (float)WQ_MACHEP;
@@ -425,6 +530,7 @@ lmwarp_kernel(const WarpArgs a) {
         __syncwarp();
         if (a.drain_grace > 0 && __any_sync(0xffffffffu, exhausted)) ++drained_ticks;
         const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+        bool fresh = false;                                 // this lane was handed a new window in this tick
         if (want) {
             const int leader = __ffs(want) - 1;
             unsigned long long base = 0;
@@ -458,8 +564,7 @@ lmwarp_kernel(const WarpArgs a) {
                             y[j] = x[j];
                         }
                     } else {
-#pragma unroll 1
-                        for (int q = 0; q < P; ++q) sd[q * TPB] = w_ld_dbl(a.windows, a.wdtype, (size_t)idx * P + q);
+                        fresh = true;                                  // pixels: loaded by the whole warp below
                         lim.lo = a.lo + idx * WNP; lim.hi = a.hi + idx * WNP;
                         lim.qll = 0; lim.qul = 0;
 #pragma unroll
@@ -498,16 +603,55 @@ lmwarp_kernel(const WarpArgs a) {
                 }
             }
         }
+        if (!PFLIB && want) {
+            // The pixels of every newly claimed window are fetched by the WHOLE warp, coalesced (lane k takes elements
+            // k, k + 32, ...): a lane copying its own 121 pixels one after the other kept the other 31 lanes waiting for
+            // 121 dependent round trips per refill -- with ~2 refills per warp and tick that was most of the kernel's time
+            unsigned needm = __ballot_sync(0xffffffffu, fresh);
+            while (needm) {
+                const int w = __ffs(needm) - 1;
+                needm &= needm - 1u;
+                const long long iw = __shfl_sync(0xffffffffu, idx, w);
+                double v[(P + 31) / 32];
+#pragma unroll
+                for (int k = 0; k < (P + 31) / 32; ++k) {
+                    const int q = k * 32 + (int)lane;
+                    v[k] = (q < P) ? w_ld_dbl(a.windows, a.wdtype, (size_t)iw * P + q) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < (P + 31) / 32; ++k) {
+                    const int q = k * 32 + (int)lane;
+                    if (q < P) {
+                        if (COOP) wpx[w * COOP_PSTR + q] = (float)v[k];
+                        else s_d[q * TPB + (tid & ~31) + w] = v[k];
+                    }
+                }
+            }
+            __syncwarp();
+        }
         if (__ballot_sync(0xffffffffu, active) == 0u) {
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;      // queue drained and nothing running
             continue;                                                    // (a refill can end at once: status 0)
         }
 
+        if (COOP) {
+            __syncwarp();                                                   // refilled pixel rows are visible to the groups
+            coop_pass<WIN, !PFLIB>(__ballot_sync(0xffffffffu, active), y, wpx, wacc, wss, lane);
+        }
         if (active) {
             // -------------------------------------------------------------- pass at the trial point
             float An[WNT], gn[WNP];
             double ss;
-            w_pass<WIN, TPB, !PFLIB, PFLIB && WIN == 5 && WRECUR>(y, sd, An, gn, ss);                      // y == x on the first tick of a fit
+            if (COOP) {
+                An[0] = (float)P;
+#pragma unroll
+                for (int i = 1; i < WNT; ++i) An[i] = wacc[lane * COOP_ASTR + i];
+#pragma unroll
+                for (int i = 0; i < WNP; ++i) gn[i] = wacc[lane * COOP_ASTR + WNT + i];
+                ss = wss[lane];
+            } else {
+                w_pass<WIN, TPB, !PFLIB, PFLIB && WIN == 5 && WRECUR>(y, sd, An, gn, ss);                  // y == x on the first tick of a fit
+            }
             if (mode != MODE_RESUME) ++nfev;
 
             bool have_new = false;
@@ -843,9 +987,11 @@ long long warp_scratch_bytes(long long n) { return 64 + (long long)(sizeof(PrepR
 
 // Persistent launch(es) of one kernel flavour: phase 1 over every fit (parked after `park_after`
 // passes when that is set), phase 2 over the parked fits.
-template <int WIN, int TPB, int MINB, bool PFLIB>
+template <int WIN, int TPB, int MINB, bool PFLIB, bool COOP = false>
 static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
+    constexpr size_t smem = COOP
+        ? (size_t)(WNT + WNP) * TPB * sizeof(float) + (size_t)(TPB / 32) * (32 * sizeof(double) + 32 * (COOP_PSTR + COOP_ASTR) * sizeof(float))
+        : (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
     // function attributes and occupancy are per device: cached per device ordinal (one process may drive several
     // GPUs from several host threads -- psfio.parallel_image_batch does)
     static std::atomic<int> per_sm_dev[64];
@@ -853,9 +999,9 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
     FSQ_CUDA_CHECK(cudaGetDevice(&dev));
     int per_sm = (dev >= 0 && dev < 64) ? per_sm_dev[dev].load(std::memory_order_acquire) : 0;
     if (per_sm == 0) {
-        FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB>, TPB, smem) != cudaSuccess || v < 1) v = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP>, TPB, smem) != cudaSuccess || v < 1) v = 1;
         per_sm = v;
         if (dev >= 0 && dev < 64) per_sm_dev[dev].store(v, std::memory_order_release);
     }
@@ -869,7 +1015,7 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
     // finishes them packed into a few blocks
     const int park = a.o.park_after;
     a.cap = park > 0 ? park : 0; a.drain_grace = park < 0 ? -park : 0; a.resume = 0;
-    lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks, TPB, smem, st>>>(a);
+    lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP><<<(unsigned)blocks, TPB, smem, st>>>(a);
     FSQ_LAUNCH_CHECK();
     if (park != 0) {
         FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
@@ -878,7 +1024,7 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
         // whatever the caller has queued on other streams (the next batch's detection and phase 1)
         const long long want2 = park < 0 ? 16 : sm_count();
         const long long blocks2 = blocks < want2 ? blocks : want2;
-        lmwarp_kernel<WIN, TPB, MINB, PFLIB><<<(unsigned)blocks2, TPB, smem, st>>>(a);
+        lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP><<<(unsigned)blocks2, TPB, smem, st>>>(a);
         FSQ_LAUNCH_CHECK();
     }
     return FSQ_OK;
@@ -943,7 +1089,13 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     int rc;
     a.o = o;
     if (win == 5) rc = launch_warp<5, 128, 2, false>(a, 0, head, st);
-    else if (win == 11) rc = launch_warp<11, 64, 3, false>(a, 0, head, st);
+    // 11x11: thread per window by default.  warps_per_sm == -2 selects the sub-warp variant (cooperative pass, COOP): it
+    // was built to the north_star's "sub-warp per spot" description and measured on B200 -- 2.3x SLOWER on 200 000
+    // windows (21 vs 8.9 ms): with all lanes busy a thread-per-window tick is already lane-efficient (9.3 k warp
+    // instructions per 32 windows), the transposed pass spends 21 k (per-round set-up, 111 shuffles per round, the
+    // serial phase unchanged); it only wins while a warp has a few long fits left.  DESIGN.md section 4.3b.
+    else if (win == 11) rc = (o.warps_per_sm == -2) ? launch_warp<11, 64, 4, false, true>(a, 0, head, st)
+                                                    : launch_warp<11, 64, 3, false>(a, 0, head, st);
     else { set_error("the FAST solver takes 5x5 or 11x11 windows (got %d)", win); rc = FSQ_E_ARG; }
     cudaFreeAsync(scratch, st);
     if (rc != FSQ_OK) return rc;

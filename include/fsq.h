@@ -111,7 +111,11 @@ typedef struct fsq_lm_opts {
                            most of every SM to launches queued on other streams: with several batches in
                            flight (engine.FieldStream) each thread then works through many more fits, so
                            far fewer warp-ticks are spent on half-empty warps waiting for their last long
-                           fit, and one batch's tail runs underneath the other batches' bulk.        */
+                           fit, and one batch's tail runs underneath the other batches' bulk.
+                           -2 (fsq_gaussfit_batch, 11x11 windows only): the sub-warp variant of the 11x11 kernel
+                           (8 lanes per window in the pass, shuffle reductions) instead of one thread per window;
+                           same algorithm, different summation order; measured slower, kept as a
+                           cross-check.                                                               */
 } fsq_lm_opts;
 
 /* Solvers behind the two fit entry points.
