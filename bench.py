@@ -511,6 +511,48 @@ def run_ours(args):
                   "value": pp.total() / (e0.elapsed_time(e1) * 1e-3), "unit": "fits/s", "ms_per_40_frames": e0.elapsed_time(e1)}
         del pp
 
+    # ---- BASELINE configs[3] beside the headline (N = 1 only): 2048x2048 frames at ~20 000 spots through the same
+    #      pipeline, and the fitter-bound batch of 11x11 windows cut from such a frame (gaussfit default arguments)
+    other = None
+    if world == 1 and not args.no_other_configs:
+        from fluorosequencingimageanalysis_b200 import synth
+        big, cr, cc, _ = synth.synth_frame_with_truth(4, H=2048, W=2048, n_spots=20000)
+        frames4 = np.stack(synth.dihedral_variants(big)[:4])
+        f4 = torch.from_numpy(frames4.view(np.int16)).view(torch.uint16).to(dev)
+        p4 = engine.FieldPipeline(4, 2048, 2048, dtype=torch.uint16, faithful=faithful, solver=solver, consolidate=True,
+                                  warps_per_sm=0)
+        p4.run(f4)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            p4.run(f4)
+        e1.record()
+        e1.synchronize()
+        ms4 = e0.elapsed_time(e1) / 5.0
+        n4, m4 = p4.total(), p4.total_psfs()
+        del p4
+        win = synth.cut_windows(big, cr, cc, 11)
+        wd = torch.from_numpy(np.concatenate([win] * (-(-200000 // len(win))))[:200000]).to(dev)
+        res11 = {}
+        for sv in ("fast", "minpack"):
+            wsub = wd if sv == "fast" else wd[:20000]
+            engine.gaussfit_default_batch(wsub, solver=sv, faithful=(sv == "minpack"))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r11, _ = engine.gaussfit_default_batch(wsub, solver=sv, faithful=(sv == "minpack"))
+            e1.record()
+            e1.synchronize()
+            res11[sv] = {"windows": int(wsub.shape[0]), "ms": e0.elapsed_time(e1), "fits_per_s": wsub.shape[0] / (e0.elapsed_time(e1) * 1e-3),
+                         "mean_niter": float(r11.niter.double().mean().item()), "status_gt0": float((r11.status > 0).double().mean().item())}
+        other = {"configs[3] frames": {"what": "4 frames 2048x2048 x ~20 000 spots, detection + 5x5 fits + metrics + consolidation, one stream",
+                                       "candidates": n4, "final_psfs": m4, "ms": ms4, "fits_per_s": n4 / (ms4 * 1e-3), "frames_per_s": 4 / (ms4 * 1e-3)},
+                 "configs[3] 11x11 windows": {"what": "windows cut around the spots of that frame (neighbours inside most windows), gaussfit default "
+                                                      "arguments, moments start values on the device (fsq_moments) inside the timed call",
+                                              "fast": res11["fast"], "minpack_faithful": res11["minpack"]}}
+        del wd, f4
+
     # ---- max over ranks, sum of work
     if world > 1:
         tt = torch.tensor([ms_total, e2e_s * 1e3, weak[0] if weak else 0.0, -pcie["h2d_gbs"], -pcie["d2h_gbs"]],
@@ -642,6 +684,8 @@ def run_ours(args):
     if weak:
         line["weak_scaling"] = {"value": world * weak[1] / (weak[0] * 1e-3), "unit": "fits/s", "steps": weak[2],
                                 "note": "every rank runs whole 800-field steps (resident inputs), max over ranks"}
+    if other is not None:
+        line["other_configs"] = other
     if parity is not None:
         line["parity_solver"] = parity
     if cpu is not None:
@@ -667,6 +711,7 @@ def main():
     ap.add_argument("--warps-per-sm", type=int, default=4, choices=[0, 1, 2, 4, 8],
                     help="fsq_lm_opts.warps_per_sm: warps per SM of ONE batch's LM launch (scheduling only; 0 = fill the SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[3] side measurements (N = 1)")
     ap.add_argument("--launch-fields", type=int, default=LAUNCH_FIELDS,
                     help="fields (x 10 cycles) one pass of the kernels processes: a larger launch amortises the drain of each "
                          "LM launch's last long fits")

@@ -20,7 +20,7 @@ FSQ_OK, FSQ_E_ARG, FSQ_E_CAPACITY, FSQ_E_CUDA, FSQ_E_RANGE = 0, -1, -2, -3, -4
 EXPORTED = ["fsq_version", "fsq_last_error", "fsq_detect_scratch_bytes", "fsq_detect",
             "fsq_detect_flags", "fsq_detect_copy_cm32", "fsq_lm_default_opts",
             "fsq_gaussfit_batch", "fsq_gaussfit_batch_ex", "fsq_gaussfit_batch_trace", "fsq_fit_candidates", "fsq_fit_scratch_bytes",
-            "fsq_metrics", "fsq_illumina_s_n", "fsq_photometry", "fsq_moments", "fsq_consolidate", "fsq_consolidate_scratch_bytes", "fsq_pack_psfs", "fsq_pack_psfs_scratch_bytes", "fsq_track_centroid", "fsq_track_greedy", "fsq_track_greedy_scratch_bytes",
+            "fsq_metrics", "fsq_illumina_s_n", "fsq_photometry", "fsq_moments", "fsq_consolidate", "fsq_consolidate_scratch_bytes", "fsq_pack_psfs", "fsq_pack_psfs_scratch_bytes", "fsq_track_centroid", "fsq_track_greedy", "fsq_track_greedy_scratch_bytes", "fsq_phase_correlate", "fsq_phase_correlate_scratch_bytes",
             "fsq_fma_peak"]
 
 
@@ -102,6 +102,10 @@ def load():
     L.fsq_track_greedy_scratch_bytes.argtypes = [i32, i32, i32, i64]
     L.fsq_track_greedy.restype = i32
     L.fsq_track_greedy.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, dbl, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.fsq_phase_correlate_scratch_bytes.restype = i64
+    L.fsq_phase_correlate_scratch_bytes.argtypes = [i32, i32, i32, i32]
+    L.fsq_phase_correlate.restype = i32
+    L.fsq_phase_correlate.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, i64, vp]
     L.fsq_fma_peak.restype = i32
     L.fsq_fma_peak.argtypes = [i32, _c.POINTER(dbl), vp]
     if L.fsq_version() != FSQ_VERSION:

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libfsq.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["fsq_api.cu", "fsq_detect.cu", "fsq_lmfit.cu", "fsq_lmfast.cu", "fsq_lmwarp.cu", "fsq_consolidate.cu", "fsq_track.cu"]
+SOURCES = ["fsq_api.cu", "fsq_detect.cu", "fsq_lmfit.cu", "fsq_lmfast.cu", "fsq_lmwarp.cu", "fsq_consolidate.cu", "fsq_track.cu", "fsq_register.cu"]
 HEADERS = ["fsq_common.cuh", "fsq_median.cuh", "fsq_median_pair.cuh", "fsq_chol7.cuh", os.path.join("..", "..", "include", "fsq.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -64,7 +64,10 @@ def build(force=False, verbose=False):
         log.append("== %s ==\n%s" % (src, out))
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    # cuFFT (the two 2-D FFTs of phase_correlate, fsq_register.cu) is the one library libfsq.so links
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-L" + cuda_lib, "-lcufft",
+                                                 "-Xlinker", "-rpath=" + cuda_lib]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         raise RuntimeError("link failed:\n" + out.stdout)

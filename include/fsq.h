@@ -310,6 +310,21 @@ int fsq_track_greedy(const double* spot_hw, const int32_t* seg_start, const doub
                      double spot_radius, int32_t* anc, int32_t* desc, int32_t* bin_hw, uint8_t* discarded,
                      int32_t* flags, void* scratch, int64_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Frame registration -- replaces phase_correlate.phase_correlate (phase_correlate.py:11-196; caller
+ * SequenceExperiment.offsets_from_frames, flexlibrary.py:1717-1741) for n_pairs image pairs in one call.
+ *  ref, reg   [n_pairs, rows, cols] of `dtype_code` (any FSQ_* code); the two may overlap (consecutive frames of one
+ *             stack: reg = ref + one frame)
+ *  out        [n_pairs, 4] float64: row_shift, col_shift, error, diffphase -- the reference's return tuple
+ *  upsample_factor = 1: whole-pixel registration; > 1: the matrix-multiply DFT on a ceil(1.5 usf)^2 grid around the peak
+ * The two forward and the inverse 2-D FFT are cuFFT Z2Z transforms (complex128 like numpy.fft); everything else --
+ * spectrum product, numpy's complex argmax, twiddle tables, the two DFT products, error / phase -- are kernels of this
+ * library.  cuFFT plans are cached per (device, rows, cols, n_pairs); scratch is caller-owned.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fsq_phase_correlate_scratch_bytes(int n_pairs, int rows, int cols, int upsample_factor);
+int fsq_phase_correlate(const void* ref, const void* reg, int dtype_code, int n_pairs, int rows, int cols,
+                        int upsample_factor, double* out, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Fit-quality metrics for arbitrary (sub_img, fit_img) pairs -- pflib.py:463-473 and
  * illumina_s_n pflib.py:261-281.  sub [n,25] int64, fit [n,25] float64 -> out [n,3] (r_2, rmse, s_n) */
 int fsq_metrics(const int64_t* sub, const double* fit, int64_t n, double* out, void* stream);

@@ -1,6 +1,6 @@
-"""GPU parity: the phase_correlate mirror (cuFFT / cuBLAS through torch) against outputs of the reference's own
-phase_correlate.py (tests/golden/phase_correlate.npz).  Shifts exact (they are multiples of 1/upsample_factor);
-error to 1e-6 absolute (1 - |CC|^2/(rg rf) cancels to ~1e-8 for aligned frames), diffphase to 1e-9."""
+"""GPU parity: the phase_correlate mirror (fsq_phase_correlate: cuFFT for the FFTs, own kernels for the rest) against outputs
+of the reference's own phase_correlate.py (tests/golden/phase_correlate.npz).  Shifts exact (they are multiples of
+1/upsample_factor); error to 1e-6 absolute (1 - |CC|^2/(rg rf) cancels to ~1e-8 for aligned frames), diffphase to 1e-9."""
 import numpy as np
 import pytest
 
@@ -35,3 +35,22 @@ def test_offsets_from_frames_batches_consecutive_pairs():
     for f in range(3):
         assert off[f + 1] == pc.phase_correlate(stack[f], stack[f + 1], 20)[:2]
     assert off[1] == (-0.35, 1.6) and off[2] == (0.35, -1.6)
+
+
+def test_phase_correlate_batch_shapes_dtypes_and_odd_sizes():
+    """The C entry point directly: float64 and uint16 inputs give the same answer, odd and rectangular frames, upsample
+    factors 1 / 7 / 20, a batch equals its pairs one by one."""
+    from fluorosequencingimageanalysis_b200 import phase_correlate as pc, synth
+    pairs = [synth.shifted_pair(11 + k, 97, 130, 0.4 * k - 1.0, 1.7 - 0.6 * k, 40) for k in range(4)]
+    ref = np.stack([p[0] for p in pairs])
+    reg = np.stack([p[1] for p in pairs])
+    for usf in (1, 7, 20):
+        r, c, e, d = (v.cpu().numpy() for v in pc.phase_correlate_batch(ref, reg, usf))
+        r64, c64, e64, d64 = (v.cpu().numpy() for v in pc.phase_correlate_batch(ref.astype(np.float64), reg.astype(np.float64), usf))
+        assert np.array_equal(r, r64) and np.array_equal(c, c64) and np.array_equal(e, e64) and np.array_equal(d, d64)
+        for k in range(4):
+            one = pc.phase_correlate(ref[k], reg[k], usf)
+            assert one == (r[k], c[k], e[k], d[k])
+        if usf == 20:                                    # the drift that was put in comes back to 1/20 px
+            for k in range(4):
+                assert abs(-r[k] - (0.4 * k - 1.0)) <= 0.05 + 1e-12 and abs(-c[k] - (1.7 - 0.6 * k)) <= 0.05 + 1e-12
