@@ -206,27 +206,46 @@ constexpr int PSTRIP = 8;                         // output rows per thread in t
 #ifndef DETECT_MEDIAN_DEFAULT
 #define DETECT_MEDIAN_DEFAULT 2                   // see detect_cm_packed_kernel
 #endif
+// Threads per block of the packed kernel.  The median stage has (PMH / 2) (PMW / 2) = 612 work items: 256 threads need
+// three sweeps with 20 % of the last one idle, 320 threads two sweeps with 4 % idle (the correlation stage then uses
+// the first 256 threads: 64 columns x 4 strips).
+#ifndef DETECT_NTP
+#define DETECT_NTP 320
+#endif
+constexpr int NTP = DETECT_NTP;
+static_assert(NTP >= 256 && NTP % 32 == 0, "the correlation stage maps 256 threads onto the tile");
 
 // MEDIAN: 0 = one window pair per step (99-comparator network); 1 = two vertically adjacent window pairs per step
 // (fsq_median_pair.cuh); 2 = the same on row windows sorted once by a pre-pass into shared memory (each sorted row
 // window serves the five output rows that contain it)
 template <typename PixT, bool RING, int MEDIAN>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NTP)
 detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp,
                         uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums) {
     constexpr bool PAIR = (MEDIAN == 1);
     __shared__ unsigned raw2[PRH * (PRW / 2)];        // u16 pairs
     __shared__ unsigned srow[MEDIAN == 2 ? PRH * (PMW / 2) * 5 : 1];      // sorted 5-pixel row windows of pixel pairs
     __shared__ __align__(16) unsigned short mf[PMH * PMW];
-    __shared__ unsigned long long red[4][NT / 32];
+    __shared__ unsigned long long red[4][NTP / 32];
 
     const int tid = threadIdx.x;
     const int frame = blockIdx.z;
     const int ty0 = blockIdx.y * PTH, tx0 = blockIdx.x * PTW;
     const PixT* img = frames + size_t(frame) * H * W;
 
-    // stage the raw tile (reflected at the image border), two pixels per word
-    for (int idx = tid; idx < PRH * (PRW / 2); idx += NT) {
+    // stage the raw tile, two pixels per word.  Interior tiles of 16-bit frames: four pixels per 64-bit load (the tile's
+    // raw origin tx0 - 4 is a multiple of four pixels and rows are 8-byte aligned when W % 4 == 0); border tiles
+    // reflect index by index
+    const bool interior = (sizeof(PixT) == 2) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 7u) == 0) && (tx0 >= 4) && (tx0 + PTW + 4 <= W) && (ty0 >= 4) && (ty0 + PTH + 4 <= H);
+    if (interior) {
+        for (int idx = tid; idx < PRH * (PRW / 4); idx += NTP) {
+            const int ry = idx / (PRW / 4), rq = idx - ry * (PRW / 4);
+            const uint2 v = *reinterpret_cast<const uint2*>(img + size_t(ty0 - 4 + ry) * W + (tx0 - 4) + 4 * rq);
+            raw2[ry * (PRW / 2) + 2 * rq] = v.x;
+            raw2[ry * (PRW / 2) + 2 * rq + 1] = v.y;
+        }
+    } else
+    for (int idx = tid; idx < PRH * (PRW / 2); idx += NTP) {
         const int ry = idx / (PRW / 2), rx = (idx - ry * (PRW / 2)) * 2;
         const int gy = reflect_idx(ty0 - 4 + ry, H);
         const int gx0 = reflect_idx(tx0 - 4 + rx, W), gx1 = reflect_idx(tx0 - 4 + rx + 1, W);
@@ -237,7 +256,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
 
     // background removal for pixel pairs: mf = v - min(median, v); zero outside the image
     if (MEDIAN == 2) {
-        for (int idx = tid; idx < PRH * (PMW / 2); idx += NT) {               // pre-pass: sort every row window once
+        for (int idx = tid; idx < PRH * (PMW / 2); idx += NTP) {               // pre-pass: sort every row window once
             const int ry = idx / (PMW / 2), mxp = idx - ry * (PMW / 2);
             const unsigned* row = raw2 + ry * (PRW / 2) + mxp;
             const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
@@ -248,7 +267,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
             for (int k = 0; k < 5; ++k) srow[idx * 5 + k] = r[k].v;
         }
         __syncthreads();
-        for (int idx = tid; idx < (PMH / 2) * (PMW / 2); idx += NT) {
+        for (int idx = tid; idx < (PMH / 2) * (PMW / 2); idx += NTP) {
             const int mp = idx / (PMW / 2), mxp = idx - mp * (PMW / 2);
             const int my = 2 * mp, mx = 2 * mxp;
             U16x2 p[30];
@@ -275,7 +294,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
         // only the middle six can be either median -- fsq_median_pair.cuh (generated, verified on all 0/1 inputs):
         // 108 instead of 198 min/max per window
         static_assert(PMH % 2 == 0 && PRH >= PMH + 4, "row pairs need an even mf tile");
-        for (int idx = tid; idx < (PMH / 2) * (PMW / 2); idx += NT) {
+        for (int idx = tid; idx < (PMH / 2) * (PMW / 2); idx += NTP) {
             const int mp = idx / (PMW / 2), mx = (idx - mp * (PMW / 2)) * 2;
             const int my = 2 * mp;
             U16x2 p[30];
@@ -304,7 +323,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
             }
         }
     } else
-    for (int idx = tid; idx < PMH * (PMW / 2); idx += NT) {
+    for (int idx = tid; idx < PMH * (PMW / 2); idx += NTP) {
         const int my = idx / (PMW / 2), mx = (idx - my * (PMW / 2)) * 2;      // mf coords of the pair's first pixel
         U16x2 p[25];
 #pragma unroll
@@ -330,7 +349,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
 
     // correlation down column strips, clamp, store, exact moments
     unsigned long long s1 = 0, saa = 0, sab = 0, sbb = 0, bad = 0;
-    {
+    if (tid < PTW * (PTH / PSTRIP)) {
         const int ox = tid & (PTW - 1);                // 64 columns
         const int oy0 = (tid / PTW) * PSTRIP;          // 4 strips of 8 rows
         const int gx = tx0 + ox;
@@ -393,7 +412,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
     __syncthreads();
     if (tid < 4) {
         unsigned long long t = 0;
-        for (int w = 0; w < NT / 32; ++w) t += red[tid][w];
+        for (int w = 0; w < NTP / 32; ++w) t += red[tid][w];
         atomicAdd(&sums[size_t(frame) * NSUM + tid], t);
     }
 }
@@ -546,7 +565,7 @@ static int launch_cm(const void* frames, int F, int H, int W, const KParam& kp, 
         // developer switch (tests): FSQ_DETECT_PAIR = 0 / 1 / 2 selects the median formulation (see the kernel)
         static const int median = getenv("FSQ_DETECT_PAIR") ? atoi(getenv("FSQ_DETECT_PAIR")) : DETECT_MEDIAN_DEFAULT;
         const bool ring = is_ring_template(kp);
-#define FSQ_LAUNCH_PACKED(R, M) detect_cm_packed_kernel<PixT, R, M><<<grid, NT, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums)
+#define FSQ_LAUNCH_PACKED(R, M) detect_cm_packed_kernel<PixT, R, M><<<grid, NTP, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums)
         if (ring) { if (median == 2) FSQ_LAUNCH_PACKED(true, 2); else if (median == 1) FSQ_LAUNCH_PACKED(true, 1); else FSQ_LAUNCH_PACKED(true, 0); }
         else      { if (median == 2) FSQ_LAUNCH_PACKED(false, 2); else if (median == 1) FSQ_LAUNCH_PACKED(false, 1); else FSQ_LAUNCH_PACKED(false, 0); }
 #undef FSQ_LAUNCH_PACKED
