@@ -628,7 +628,7 @@ def run_ours(args):
                         "detection / consolidation kernels: the kernel's sustained rate, a lower bound; *_lone_launch = the fit kernels "
                         "of one 200-frame launch timed alone by CUDA events. Residual / chi^2 are FP64, Jacobian / normal equations / "
                         "Cholesky FP32, so the FP32 peak is an upper bound the kernel cannot reach"}
-    alu_pct, alu_src = None, "profiles/r01i_detect_kernel.txt"
+    alu_pct, alu_src = None, "profiles/r02_detect_kernel.txt"
     for cand_src in ("profiles/r02_detect_kernel.txt", alu_src):
         try:
             for ln in open(os.path.join(ROOT, cand_src)):

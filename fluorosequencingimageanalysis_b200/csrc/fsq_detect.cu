@@ -208,9 +208,12 @@ constexpr int PSTRIP = 8;                         // output rows per thread in t
 #endif
 // Threads per block of the packed kernel.  The median stage has (PMH / 2) (PMW / 2) = 612 work items: 256 threads need
 // three sweeps with 20 % of the last one idle, 320 threads two sweeps with 4 % idle (the correlation stage then uses
-// the first 256 threads: 64 columns x 4 strips).
+// the first 256 threads).  Measured on B200 (profiles/r02_detect_kernel_320threads.txt): the same 105 us per 42-frame
+// chunk either way -- with 256 threads the ALU pipe is 79 % busy and is the limit, with 320 threads it is 61 % busy and
+// the block-wide barriers between the stages are (10 warps per barrier) -- so the idle lanes of the last sweep cost
+// nothing: other warps use the pipe.  256 it stays.
 #ifndef DETECT_NTP
-#define DETECT_NTP 320
+#define DETECT_NTP 256
 #endif
 constexpr int NTP = DETECT_NTP;
 static_assert(NTP >= 256 && NTP % 32 == 0, "the correlation stage maps 256 threads onto the tile");
