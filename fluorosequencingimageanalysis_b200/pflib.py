@@ -23,11 +23,15 @@ default_correlation_matrix = DEFAULT_CORRELATION_MATRIX.copy()      # pflib.py:4
 FAITHFUL = True
 
 #: which LM kernel the drop-in entry points run (fsq.h FSQ_SOLVER_*):
-#:   "minpack" -- the reference's algorithm operation for operation (with FAITHFUL: bug for bug);
-#:                this is what makes ``find_peptides`` return what the reference returns
-#:   "fast"    -- the production fitter (analytic Jacobian, normal equations; ~250x faster): equal to
-#:                the reference wherever the reference's own trajectory is a clean Gauss-Newton one,
-#:                a lower chi^2 elsewhere (DESIGN.md "Parity")
+#:   "minpack" -- the reference's algorithm operation for operation (with FAITHFUL: its qrsolv defect included).
+#:                Measured against reference-generated fits (tests/test_gpu_parity_table.py, four golden sets): equal
+#:                to the reference on 0.94 of the fits whose reference trajectory is a clean one, 0.76 of the fits the
+#:                reference accepts, 0.60 of all candidates, 0.88-0.90 of the final PSF keys -- the reference itself
+#:                reproduces 0.85 / 0.69 / 0.54 of its own answers when exp() is perturbed by one ulp (the pflib call
+#:                starts theta on its bound with equal widths, so the first step is rounding noise)
+#:   "fast"    -- the production fitter (analytic Jacobian, normal equations; ~600x faster): 0.98 / 0.59 / 0.35 and
+#:                0.79-0.84 of the final keys on the same sets; equal to the reference wherever the reference's answer
+#:                is reproducible and its trajectory clean, the clean algorithm's constrained minimum elsewhere
 SOLVER = "minpack"
 
 
