@@ -375,3 +375,28 @@ def test_fast_11x11_sub_warp_variant_matches_the_reference_too():
         assert ok[robust].mean() >= 0.99 and (s > 0).all()
         assert (chi <= g["ref_fnorm"] * (1 + 1e-6)).mean() >= 0.97
         assert same[robust].mean() >= 0.99
+
+
+def test_field_stream_partial_batches_equal_single_calls():
+    """A FieldStream built for F frames per batch also takes shorter batches (the last chunk of a rank's field block in
+    bench.py): candidates, fits and the final PSF records equal what separate calls return, and a full batch after a
+    partial one in the same slot is not disturbed by it."""
+    engine, _, synth, _ = _mods()
+    import torch
+    stacks = [synth.synth_timetrace(80 + i, n_frames=n, H=128, W=160, n_spots=40) for i, n in enumerate((4, 2, 4, 1, 3))]
+    fs = engine.FieldStream(4, 128, 160, dtype=torch.uint16, depth=2, host_io=True, fetch="psfs", solver="fast", faithful=False)
+    for st in stacks:
+        host = torch.from_numpy(st.view(np.int16)).view(torch.uint16).pin_memory()
+        t = fs.submit(host)
+        n, m, psf_int, psf_fit, psf_base = fs.end_fetch(t)
+        F = st.shape[0]
+        assert psf_base.shape[0] == F + 1 and int(psf_base[F]) == m
+        want = engine.find_peptides_batch(st, solver="fast", faithful=False, to_host=False)
+        assert n == int(want.cand_hw.shape[0])
+        cons = engine.consolidate_batch(want.cand_hw, want.cand_frame, want.fit, n, F)
+        pk = engine.pack_psfs_batch(cons, want.cand_frame, want.fit, n, F)
+        mm = int(pk.base[F].item())
+        assert mm == m
+        assert np.array_equal(pk.ints[:mm].cpu().numpy(), psf_int.numpy())
+        assert np.array_equal(pk.fit[:mm].cpu().numpy().view(np.int64), psf_fit.numpy().view(np.int64))
+        assert np.array_equal(pk.base.cpu().numpy(), psf_base.numpy())

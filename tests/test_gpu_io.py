@@ -76,3 +76,38 @@ def test_parallel_image_batch_equals_image_batch(tmp_path):
         pflib.parallel_image_batch(paths, num_processes=2.5)
     assert pflib.parallel_image_batch(paths[:1], timestamp_epoch=1461000020, num_processes=4).keys() == \
         pflib.image_batch(paths[:1], timestamp_epoch=1461000020).keys()
+
+
+def test_image_batch_goes_through_bounded_chunks_and_loses_only_the_failing_image(tmp_path, monkeypatch):
+    """image_batch reads lazily and sends bounded same-shape chunks to the device (psfio.BATCH_MAX_FRAMES); when a chunk
+    fails as a whole every image of it is retried on its own, so only the failing image is skipped -- the reference's
+    granularity (pflib.py:957-996)."""
+    from fluorosequencingimageanalysis_b200 import pflib, psfio, engine
+    paths, imgs = _write_frames(tmp_path, n=5)
+    monkeypatch.setattr(psfio, "BATCH_MAX_FRAMES", 2)
+    calls = []
+    real = engine.find_peptides_batch
+
+    def spy(frames, *a, **kw):
+        f = np.asarray(frames)
+        calls.append(f.shape[0] if f.ndim == 3 else 1)
+        return real(frames, *a, **kw)
+    monkeypatch.setattr(engine, "find_peptides_batch", spy)
+    out = pflib.image_batch(paths, timestamp_epoch=1461000010)
+    assert sorted(out.keys()) == sorted(os.path.abspath(p) for p in paths)
+    assert max(calls) <= 2 and sum(calls) == len(paths)              # 5 same-shape frames -> 2 + 2 + 1, the odd one alone
+    for p, img in zip(paths, imgs):
+        _same_psfs(pickle.load(open(out[os.path.abspath(p)][1], 'rb')), pflib.find_peptides(img))
+
+    # a batch that fails as a whole: the images are retried one by one and only the bad one is lost
+    bad_marker = imgs[1]
+
+    def flaky(frames, *a, **kw):
+        f = np.asarray(frames)
+        f3 = f if f.ndim == 3 else f[None]
+        if any(np.array_equal(x, bad_marker) for x in f3):
+            raise RuntimeError("simulated device failure")
+        return real(frames, *a, **kw)
+    monkeypatch.setattr(engine, "find_peptides_batch", flaky)
+    out2 = pflib.image_batch(paths, timestamp_epoch=1461000011)
+    assert sorted(out2.keys()) == sorted(os.path.abspath(p) for i, p in enumerate(paths) if i != 1)

@@ -3,11 +3,12 @@
 /root/reference is present in this container.  SURVEY.md App. D KAT-1 / KAT-2."""
 import glob
 import os
+import sys
 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden, detect_kwargs
+from conftest import GOLDEN, ROOT, golden, detect_kwargs
 from oracle import pflib_oracle as po
 from oracle import build_ref
 
@@ -245,3 +246,61 @@ def test_greedy_tracking_oracle_equals_reference():
             as_idx = [[None if s is None else spots[f].index(s) for f, s in enumerate(tr)] for tr in ref]
             assert as_idx == want, (radius, offsets[1])
     assert any(t[0] is not None and t[1] is None and any(v is not None for v in t[2:]) for t in want)      # a trace that skips a frame
+
+
+@pytest.mark.parametrize("case", ["seed3", "dense1000", "d2048"])
+def test_new_fit_goldens_are_pinned_to_the_oracle(case):
+    """The round-2 reference-fit goldens (second seed, 1000-spot density, the dense 2048^2 frame): the frame regenerates to
+    the stored hash, the candidate list equals the oracle's, and both oracle flavours reproduce the stored reference /
+    clean answers bit for bit on a seeded sample (the whole set was checked when the golden was made)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_parity_table import _frame
+    g = golden("fits5_%s.npz" % case)
+    img = _frame(case)
+    assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == str(g["img_sha"])
+    assert bool(g["oracle_equals_ref"].all())
+    if case != "d2048":                                  # (the oracle's detection of the 2048^2 frame runs in the GPU suite)
+        assert np.array_equal(np.array(po.psf_candidates(img), dtype=np.int32), g["cands"])
+    rng = np.random.default_rng(5)
+    for i in rng.choice(len(g["cands"]), 10, replace=False):
+        h, w = g["cands"][i]
+        sub = img[h - 2:h + 3, w - 2:w + 3].astype(np.int64)
+        _, res = po.fit_2d_gaussian(sub, faithful=True, return_result=True)
+        assert np.array_equal(res.params, g["ref_params"][i])
+        assert (res.status, res.niter, res.nfev, res.n_qrsolv) == (g["ref_status"][i], g["ref_niter"][i], g["ref_nfev"][i], g["n_qrsolv"][i])
+        _, cl = po.fit_2d_gaussian(sub, faithful=False, return_result=True)
+        assert np.array_equal(cl.params, g["clean_params"][i]) and cl.status == g["clean_status"][i]
+        r_2, rmse, s_n = po.fit_metrics(sub, po.gauss2d(res.params, (5, 5)))
+        assert (r_2, rmse, s_n) == (g["r_2"][i], g["rmse"][i], g["s_n"][i])
+    st = golden("stable5_%s.npz" % case)
+    assert st["stable_ref"].shape == (len(g["cands"]),) and 0.2 < st["stable_ref"].mean() < 0.5
+
+
+def test_fits11_dense_golden_is_pinned_to_the_oracle():
+    g = golden("fits11_d2048.npz")
+    assert bool(g["oracle_equals_ref"].all()) and len(g["windows"]) == 400
+    for i in (3, 150, 399):
+        res, _ = po.gaussfit(g["windows"][i], faithful=True)
+        assert np.array_equal(res.params, g["ref_params"][i])
+        assert res.status == g["ref_status"][i] and res.niter == g["ref_niter"][i]
+        assert np.array_equal(np.array(po.moments(g["windows"][i]), dtype=float), g["p0"][i])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_gaussfit_variant_golden_is_the_reference_output():
+    """tests/golden/gaussfit_variants.npz holds what the reference's own gaussfit returns (spot check, live)."""
+    from oracle import make_golden
+    build_ref.build(quiet=True)
+    _, gaussfitter, _ = build_ref.load()
+    g = golden("gaussfit_variants.npz")
+    cases = make_golden.variant_cases()
+    for name in ("circle11", "fixed_centre11", "circle_noheight_err11", "pflib_fixed_theta5"):
+        side, kwf = cases[name]
+        w = (g["w11"] if side == 11 else g["w5"])[7]
+        mp = gaussfitter.gaussfit(w, returnmp=True, **kwf(w))
+        m = int(g[name + "_npar"][7])
+        assert len(mp.params) == m and np.array_equal(mp.params, g[name + "_params"][7][:m])
+        assert mp.status == g[name + "_status"][7] and mp.nfev == g[name + "_nfev"][7] and mp.dof == g[name + "_dof"][7]
+        if mp.perror is not None:
+            assert np.array_equal(mp.covar, g[name + "_covar"][7][:m, :m])
