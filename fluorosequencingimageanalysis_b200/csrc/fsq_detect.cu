@@ -218,15 +218,49 @@ constexpr int PSTRIP = 8;                         // output rows per thread in t
 constexpr int NTP = DETECT_NTP;
 static_assert(NTP >= 256 && NTP % 32 == 0, "the correlation stage maps 256 threads onto the tile");
 
+// Shared-memory rows of the staged raw tile: 80 pixels = 40 words.  The tile needs columns tx0 - 4 .. tx0 + 67 (PRW = 72),
+// but tx0 - 4 is only 8-byte aligned; a row that starts at tx0 - 8 is 16-byte aligned (tx0 is a multiple of 64, W of 8),
+// which is what the bulk-async copy engine asks for.  RO = word offset of raw column 0 inside a staged row.
+constexpr int RP = (PRW + 8) / 2;
+constexpr int RO = 2;
+
+// ---- bulk-async (TMA unit, cp.async.bulk -> UBLKCP) staging of interior raw tiles: one thread arms an mbarrier with the
+// tile's byte count, PRH threads issue one 160-byte row copy each straight into shared memory, the block waits on the
+// barrier's phase -- no register round trip, no per-thread address arithmetic.  Border tiles need scipy's reflection and
+// are staged index by index.  (The tensor-map form, cp.async.bulk.tensor / UTMALDG, traps with "illegal instruction" on
+// this pool's boxes for every descriptor tried -- tools/micro/tma_probe.cu, profiles/r02_tma_probe.txt -- the row form
+// of the same engine works.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // the async proxy sees the initialised barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
 // MEDIAN: 0 = one window pair per step (99-comparator network); 1 = two vertically adjacent window pairs per step
 // (fsq_median_pair.cuh); 2 = the same on row windows sorted once by a pre-pass into shared memory (each sorted row
 // window serves the five output rows that contain it)
 template <typename PixT, bool RING, int MEDIAN>
 __global__ void __launch_bounds__(NTP)
 detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp,
-                        uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums) {
+                        uint32_t* __restrict__ cm32, unsigned long long* __restrict__ sums, int use_bulk) {
     constexpr bool PAIR = (MEDIAN == 1);
-    __shared__ unsigned raw2[PRH * (PRW / 2)];        // u16 pairs
+    __shared__ __align__(128) unsigned raw2[PRH * RP];            // u16 pairs, rows of 80 pixels (see RP / RO)
+    __shared__ __align__(8) unsigned long long stage_bar;
     __shared__ unsigned srow[MEDIAN == 2 ? PRH * (PMW / 2) * 5 : 1];      // sorted 5-pixel row windows of pixel pairs
     __shared__ __align__(16) unsigned short mf[PMH * PMW];
     __shared__ unsigned long long red[4][NTP / 32];
@@ -236,24 +270,30 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
     const int ty0 = blockIdx.y * PTH, tx0 = blockIdx.x * PTW;
     const PixT* img = frames + size_t(frame) * H * W;
 
-    // stage the raw tile, two pixels per word.  Interior tiles of 16-bit frames: four pixels per 64-bit load (the tile's
-    // raw origin tx0 - 4 is a multiple of four pixels and rows are 8-byte aligned when W % 4 == 0); border tiles
-    // reflect index by index
-    const bool interior = (sizeof(PixT) == 2) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 7u) == 0) && (tx0 >= 4) && (tx0 + PTW + 4 <= W) && (ty0 >= 4) && (ty0 + PTH + 4 <= H);
-    if (interior) {
+    // stage the raw tile, two pixels per word.  Interior tiles of 16-bit frames: one bulk-async row copy of 80 pixels per
+    // tile row (rows start at tx0 - 8, 16-byte aligned when W % 8 == 0 and the frame base is), or -- when that alignment
+    // is not given -- four pixels per 64-bit load; border tiles reflect index by index
+    const bool inside = (sizeof(PixT) == 2) && (ty0 >= 4) && (ty0 + PTH + 4 <= H);
+    const bool bulk = use_bulk && inside && (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0) && (tx0 >= 8) && (tx0 + PTW + 8 <= W);
+    const bool interior = inside && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 7u) == 0) && (tx0 >= 4) && (tx0 + PTW + 4 <= W);
+    if (bulk) {
+        if (tid == 0) { mbar_init(&stage_bar, 1); mbar_expect_tx(&stage_bar, (unsigned)(PRH * RP * 4)); }
+        __syncthreads();                                                      // barrier armed before any copy completes on it
+        if (tid < PRH) bulk_copy_g2s(raw2 + tid * RP, img + size_t(ty0 - 4 + tid) * W + (tx0 - 8), (unsigned)(RP * 4), &stage_bar);
+        mbar_wait(&stage_bar, 0);
+    } else if (interior) {
         for (int idx = tid; idx < PRH * (PRW / 4); idx += NTP) {
             const int ry = idx / (PRW / 4), rq = idx - ry * (PRW / 4);
             const uint2 v = *reinterpret_cast<const uint2*>(img + size_t(ty0 - 4 + ry) * W + (tx0 - 4) + 4 * rq);
-            raw2[ry * (PRW / 2) + 2 * rq] = v.x;
-            raw2[ry * (PRW / 2) + 2 * rq + 1] = v.y;
+            *reinterpret_cast<uint2*>(raw2 + ry * RP + RO + 2 * rq) = v;
         }
     } else
     for (int idx = tid; idx < PRH * (PRW / 2); idx += NTP) {
-        const int ry = idx / (PRW / 2), rx = (idx - ry * (PRW / 2)) * 2;
+        const int ry = idx / (PRW / 2), rw = idx - ry * (PRW / 2), rx = rw * 2;
         const int gy = reflect_idx(ty0 - 4 + ry, H);
         const int gx0 = reflect_idx(tx0 - 4 + rx, W), gx1 = reflect_idx(tx0 - 4 + rx + 1, W);
         const unsigned lo = (unsigned)img[size_t(gy) * W + gx0], hi = (unsigned)img[size_t(gy) * W + gx1];
-        raw2[idx] = lo | (hi << 16);
+        raw2[ry * RP + RO + rw] = lo | (hi << 16);
     }
     __syncthreads();
 
@@ -261,7 +301,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
     if (MEDIAN == 2) {
         for (int idx = tid; idx < PRH * (PMW / 2); idx += NTP) {               // pre-pass: sort every row window once
             const int ry = idx / (PMW / 2), mxp = idx - ry * (PMW / 2);
-            const unsigned* row = raw2 + ry * (PRW / 2) + mxp;
+            const unsigned* row = raw2 + ry * RP + RO + mxp;
             const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
             U16x2 r[5];
             r[0].v = w0; r[1].v = __byte_perm(w0, w1, 0x5432); r[2].v = w1; r[3].v = __byte_perm(w1, w2, 0x5432); r[4].v = w2;
@@ -278,7 +318,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
             for (int i = 0; i < 6; ++i)
 #pragma unroll
                 for (int k = 0; k < 5; ++k) p[i * 5 + k].v = srow[((my + i) * (PMW / 2) + mxp) * 5 + k];
-            const unsigned v_top = raw2[(my + 2) * (PRW / 2) + mxp + 1], v_bot = raw2[(my + 3) * (PRW / 2) + mxp + 1];
+            const unsigned v_top = raw2[(my + 2) * RP + RO + mxp + 1], v_bot = raw2[(my + 3) * RP + RO + mxp + 1];
             U16x2 m_top, m_bot;
             median25_pair_sorted<U16x2>(p, m_top, m_bot);
             unsigned out[2] = {__vsubus2(v_top, m_top.v), __vsubus2(v_bot, m_bot.v)};      // max(v - med, 0) per half
@@ -303,7 +343,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
             U16x2 p[30];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const unsigned* row = raw2 + (my + i) * (PRW / 2) + (mx >> 1);
+                const unsigned* row = raw2 + (my + i) * RP + RO + (mx >> 1);
                 const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
                 p[i * 5 + 0].v = w0;
                 p[i * 5 + 1].v = __byte_perm(w0, w1, 0x5432);
@@ -331,7 +371,7 @@ detect_cm_packed_kernel(const PixT* __restrict__ frames, int H, int W, KParam kp
         U16x2 p[25];
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-            const unsigned* row = raw2 + (my + i) * (PRW / 2) + (mx >> 1);     // raw col = mx .. mx+5
+            const unsigned* row = raw2 + (my + i) * RP + RO + (mx >> 1);     // raw col = mx .. mx+5
             const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
             p[i * 5 + 0].v = w0;
             p[i * 5 + 1].v = __byte_perm(w0, w1, 0x5432);
@@ -568,7 +608,9 @@ static int launch_cm(const void* frames, int F, int H, int W, const KParam& kp, 
         // developer switch (tests): FSQ_DETECT_PAIR = 0 / 1 / 2 selects the median formulation (see the kernel)
         static const int median = getenv("FSQ_DETECT_PAIR") ? atoi(getenv("FSQ_DETECT_PAIR")) : DETECT_MEDIAN_DEFAULT;
         const bool ring = is_ring_template(kp);
-#define FSQ_LAUNCH_PACKED(R, M) detect_cm_packed_kernel<PixT, R, M><<<grid, NTP, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums)
+        // developer switch (A/B): FSQ_DETECT_BULK = 0 stages interior tiles with 64-bit loads instead of bulk-async row copies
+        static const int use_bulk = getenv("FSQ_DETECT_BULK") ? atoi(getenv("FSQ_DETECT_BULK")) : 1;
+#define FSQ_LAUNCH_PACKED(R, M) detect_cm_packed_kernel<PixT, R, M><<<grid, NTP, 0, st>>>((const PixT*)frames, H, W, kp, sc.cm32, sc.sums, use_bulk)
         if (ring) { if (median == 2) FSQ_LAUNCH_PACKED(true, 2); else if (median == 1) FSQ_LAUNCH_PACKED(true, 1); else FSQ_LAUNCH_PACKED(true, 0); }
         else      { if (median == 2) FSQ_LAUNCH_PACKED(false, 2); else if (median == 1) FSQ_LAUNCH_PACKED(false, 1); else FSQ_LAUNCH_PACKED(false, 0); }
 #undef FSQ_LAUNCH_PACKED
