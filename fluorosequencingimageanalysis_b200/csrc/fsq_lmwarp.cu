@@ -250,8 +250,8 @@ __device__ __forceinline__ void w_sincos_deg(double th, double* sn, double* cs) 
 //   G(r+1,0) = G(r,0) Kx,  with Kc, Kr, Kx = exp of the (constant) second differences.
 // Measured against an 80-bit evaluation over the whole parameter box: relative error <= 9.3e-15 (the direct
 // polynomial: 5.0e-15), four orders below what the ftol = 1e-10 test resolves.
-template <int WIN, int TPB, bool CLAMP, bool RECUR>
-__device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __restrict__ sd,
+template <int WIN, int TPB, bool CLAMP, bool RECUR, typename PXT>
+__device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __restrict__ sd,
                                        float (&A)[WNT], float (&g)[WNP], double& ss_out) {
     static_assert(!RECUR || (WIN <= 5 && !CLAMP), "forward differencing needs bounded exponents");
     const double Hh = pt[0], Aa = pt[1];
@@ -312,7 +312,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
     for (int r = 0; r < WIN; ++r) {
         const double ra = dx * cxs, rb = dx * sys;
         const float raf = (float)ra, rbf = (float)rb;
-        const double* drow = sd + r * WIN * TPB;
+        const PXT* drow = sd + r * WIN * TPB;
         dx -= 1.0;
         double Ec = Er, Gc = Grow;
         if (RECUR) { Er *= Grr; Grr *= Kr; Grow *= Kx; }
@@ -340,7 +340,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
             double E;
             if (RECUR) { E = Ec; Ec *= Gc; Gc *= Kc; }
             else E = CLAMP ? ezero * w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av)) : w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
-            const double f = drow[c * TPB] - fma(Aa, E, Hh);
+            const double f = (double)drow[c * TPB] - fma(Aa, E, Hh);
             ss = fma(f, f, ss);
             const float Ef = (float)E, ff = (float)f;
             const float AE = Af * Ef;
@@ -368,101 +368,78 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const double* __
 }
 
 // -------------------------------------------------------------------------------------------
-// Cooperative pass of the 11x11 kernel (COOP): the 121 pixels of a window are too many for one thread (254 registers,
-// 6 warps per SM, latency-bound: 5.6e7 fits/s) and too few for a warp, so the warp TRANSPOSES its work between the two
-// phases of a tick.  Pass: the 32 windows of the warp are processed four at a time by the four 8-lane groups -- lane gl
-// of a group takes pixels gl, gl + 8, ... of its group's window, at the trial point shuffled in from the window's owner
-// lane -- and the 28 + 7 FP32 sums and the FP64 chi^2 are reduced over the group by xor shuffles and left in the warp's
-// shared-memory accumulator rows.  Everything else of the tick (bookkeeping, Cholesky, lmpar, bounds) then runs one
-// thread per window as before, with all 32 lanes busy and no redundant work.  Pixels sit in shared memory as FP32
-// ([window][136]: groups read conflict-free), exact for integer camera data below 2^24.
+// Lane-group pass of the 11x11 kernel (GRP lanes per window, GRP = 2, 4 or 8): 121 pixels are too many for one thread
+// when latency matters -- a thread-per-window tick is ~9 700 dependent-ish instructions, and a window that runs to
+// maxiter = 200 (1-3 % of real 11x11 windows do, in the reference as well) keeps its warp alive for 200 of them -- and too
+// few for a warp.  Here GRP adjacent lanes own ONE window for its whole life: lane gl takes pixels gl, gl + GRP, ... of
+// the pass, the 27 + 7 FP32 sums and the FP64 chi^2 are reduced over the group by an xor butterfly (bitwise identical
+// sums in every lane of the group), and everything else of the tick -- bookkeeping, Cholesky, lmpar, bounds -- is executed
+// redundantly by all lanes of the group on identical numbers, so the group never diverges and needs no broadcast.
+// Pixels sit in shared memory as [window][128 + GRP] (the lanes of a warp read conflict-free), in FP32 when the
+// window data are narrow integers (exact), in FP64 otherwise.
 // -------------------------------------------------------------------------------------------
-constexpr int COOP_PSTR = 136;          // floats per window row of the pixel block (121 pixels, 8 (mod 32) stride)
-constexpr int COOP_ASTR = 37;           // floats per window row of the accumulator block (35 sums, odd stride)
-
-template <int WIN, bool CLAMP>
-__device__ __forceinline__ void coop_pass(const unsigned actmask, const double (&y)[WNP], const float* __restrict__ wpx,
-                                          float* __restrict__ wacc, double* __restrict__ wss, const unsigned lane) {
+template <int WIN, int G, bool CLAMP, typename PXT>
+__device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __restrict__ px, const int gl,
+                                       float (&A)[WNT], float (&g)[WNP], double& ss_out) {
     constexpr int P = WIN * WIN;
-    constexpr int SL = (P + 7) / 8;                 // pixel slots per lane
-    const unsigned grp = lane >> 3, gl = lane & 7u;
-#pragma unroll 1
-    for (int rd = 0; rd < 8; ++rd) {
-        if (((actmask >> (4 * rd)) & 0xfu) == 0u) continue;              // warp-uniform: none of the four windows is running
-        const int w = 4 * rd + (int)grp;
-        double pt[WNP];
+    constexpr int SL = (P + G - 1) / G;             // pixel slots per lane
+    static_assert(G < WIN, "one row wrap per slot");
+    const double Hh = pt[0], Aa = pt[1];
+    double sn, cs;
+    w_sincos_deg(pt[6], &sn, &cs);
+    const bool flat = CLAMP && ((pt[4] == 0.0) || (pt[5] == 0.0));     // see w_pass
+    const double ezero = flat ? 0.0 : 1.0;
+    const double iwx = (CLAMP && pt[4] == 0.0) ? 0.0 : 1.0 / pt[4], iwy = (CLAMP && pt[5] == 0.0) ? 0.0 : 1.0 / pt[5];
+    const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
+    // a(r, c) = (p3 - r) cxs - (p2 - c) sxs,  b(r, c) = (p3 - r) sys + (p2 - c) cys
+    const double a00 = fma(pt[3], cxs, -pt[2] * sxs), b00 = fma(pt[3], sys, pt[2] * cys);
+    const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
+    const float iwxf = (float)iwx, iwyf = (float)iwy;
+    const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
 #pragma unroll
-        for (int j = 0; j < WNP; ++j) pt[j] = __shfl_sync(0xffffffffu, y[j], w);
-        const double Hh = pt[0], Aa = pt[1];
-        double sn, cs;
-        w_sincos_deg(pt[6], &sn, &cs);
-        const bool flat = CLAMP && ((pt[4] == 0.0) || (pt[5] == 0.0));     // see w_pass
-        const double ezero = flat ? 0.0 : 1.0;
-        const double iwx = (CLAMP && pt[4] == 0.0) ? 0.0 : 1.0 / pt[4], iwy = (CLAMP && pt[5] == 0.0) ? 0.0 : 1.0 / pt[5];
-        const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
-        // a(r, c) = (p3 - r) cxs - (p2 - c) sxs,  b(r, c) = (p3 - r) sys + (p2 - c) cys
-        const double a00 = fma(pt[3], cxs, -pt[2] * sxs), b00 = fma(pt[3], sys, pt[2] * cys);
-        const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
-        const float iwxf = (float)iwx, iwyf = (float)iwy;
-        const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
-        float A[WNT], g[WNP];
+    for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
+    for (int i = 0; i < WNP; ++i) g[i] = 0.0f;
+    double ss = 0.0;
+    int r = 0, c = gl;                                               // pixel gl + G s = (r, c), advanced by G per slot
+#ifndef W11_UNROLL
+#define W11_UNROLL 2
+#endif
+    constexpr int UNR = W11_UNROLL;
+#pragma unroll UNR
+    for (int sl = 0; sl < SL; ++sl) {
+        const bool ok = (sl * G + gl) < P;
+        const double rd_ = (double)r, cd = (double)c;
+        const double av = fma(cd, sxs, fma(-rd_, cxs, a00));
+        const double bv = fma(-cd, cys, fma(-rd_, sys, b00));
+        const double E0 = w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
+        const double E = ok ? (CLAMP ? ezero * E0 : E0) : 0.0;
+        const double d = ok ? (double)px[sl * G] : Hh;              // beyond the window: zero residual, zero Jacobian
+        const double f = d - fma(Aa, E, Hh);
+        ss = fma(f, f, ss);
+        const float af = (float)av, bf = (float)bv;
+        const float Ef = (float)E, ff = (float)f;
+        const float AE = Af * Ef;
+        const float AEa = AE * af, AEb = AE * bf;
+        float j[WNP];
+        j[1] = -Ef;
+        j[2] = AEb * cyw - AEa * sx;
+        j[3] = AEa * cxw + AEb * sy;
+        j[4] = -AEa * af * iwxf;
+        j[5] = -AEb * bf * iwyf;
+        j[6] = -AEa * bf * krot;
+        g[0] -= ff;
 #pragma unroll
-        for (int i = 0; i < WNP; ++i) g[i] = 0.0f;
-        double ss = 0.0;
-        const float* px = wpx + w * COOP_PSTR + gl;
-        int r = 0, c = (int)gl;                                          // pixel gl + 8 s = (r, c), advanced by 8 per slot
-#pragma unroll 4
-        for (int sl = 0; sl < SL; ++sl) {
-            const bool ok = (sl * 8 + (int)gl) < P;
-            const double rd_ = (double)r, cd = (double)c;
-            const double av = fma(cd, sxs, fma(-rd_, cxs, a00));
-            const double bv = fma(-cd, cys, fma(-rd_, sys, b00));
-            const double E0 = w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
-            const double E = ok ? (CLAMP ? ezero * E0 : E0) : 0.0;
-            const double d = ok ? (double)px[sl * 8] : Hh;              // beyond the window: zero residual, zero Jacobian
-            const double f = d - fma(Aa, E, Hh);
-            ss = fma(f, f, ss);
-            const float af = (float)av, bf = (float)bv;
-            const float Ef = (float)E, ff = (float)f;
-            const float AE = Af * Ef;
-            const float AEa = AE * af, AEb = AE * bf;
-            float j[WNP];
-            j[1] = -Ef;
-            j[2] = AEb * cyw - AEa * sx;
-            j[3] = AEa * cxw + AEb * sy;
-            j[4] = -AEa * af * iwxf;
-            j[5] = -AEb * bf * iwyf;
-            j[6] = -AEa * bf * krot;
-            g[0] -= ff;
+        for (int k = 1; k < WNP; ++k) {
+            g[k] = fmaf(j[k], ff, g[k]);
+            A[wtri(k, 0)] -= j[k];
 #pragma unroll
-            for (int k = 1; k < WNP; ++k) {
-                g[k] = fmaf(j[k], ff, g[k]);
-                A[wtri(k, 0)] -= j[k];
-#pragma unroll
-                for (int l = 1; l <= k; ++l) A[wtri(k, l)] = fmaf(j[k], j[l], A[wtri(k, l)]);
-            }
-            c += 8;
-            if (c >= WIN) { c -= WIN; ++r; }
+            for (int l = 1; l <= k; ++l) A[wtri(k, l)] = fmaf(j[k], j[l], A[wtri(k, l)]);
         }
-        // reduce over the 8 lanes of the group (xor butterfly: identical sums in every lane), then each lane stores its share
-#pragma unroll
-        for (int m = 4; m >= 1; m >>= 1) {
-            ss += __shfl_xor_sync(0xffffffffu, ss, m);
-#pragma unroll
-            for (int i = 1; i < WNT; ++i) A[i] += __shfl_xor_sync(0xffffffffu, A[i], m);
-#pragma unroll
-            for (int i = 0; i < WNP; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], m);
-        }
-        float* acc = wacc + w * COOP_ASTR;
-#pragma unroll
-        for (int i = 1; i < WNT; ++i) if ((unsigned)(i & 7) == gl) acc[i] = A[i];
-#pragma unroll
-        for (int i = 0; i < WNP; ++i) if ((unsigned)((WNT + i) & 7) == gl) acc[WNT + i] = g[i];
-        if (gl == 0) wss[w] = ss;
+        c += G;
+        if (c >= WIN) { c -= WIN; ++r; }
     }
-    __syncwarp();
+    ss_out = ss;
 }
 
 enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
@@ -474,26 +451,41 @@ enum { MODE_FIRST = 0, MODE_TRIAL = 1, MODE_RESUME = 2 };
 #define WLMPAR_MAX 10      // lmpar iteration limit (mpfit.py:2148)
 #endif
 
-template <int WIN, int TPB, int MINB, bool PFLIB, bool COOP = false>
+// GRP = lanes per window (1: one thread per window; 2 / 4 / 8: lane groups, generic-window entry only, see g_pass);
+// PXT = type of the pixels in shared memory (double; float when the window data are narrow integers -- exact)
+template <int WIN, int GRP>
+struct WLayout {
+    static constexpr int P = WIN * WIN;
+    static constexpr int PSTR = ((P + 31) / 32) * 32 + GRP;       // elements per window row of the lane-group pixel block
+    template <int TPB, typename PXT>
+    __host__ __device__ static constexpr size_t pixel_bytes() {
+        return GRP == 1 ? (size_t)P * TPB * sizeof(PXT) : (((size_t)(TPB / GRP) * PSTR * sizeof(PXT) + 15) / 16) * 16;
+    }
+    template <int TPB, typename PXT>
+    __host__ __device__ static constexpr size_t smem_bytes() { return pixel_bytes<TPB, PXT>() + (size_t)(WNT + WNP) * TPB * sizeof(float); }
+};
+
+template <int WIN, int TPB, int MINB, bool PFLIB, int GRP = 1, typename PXT = double>
 __global__ void __launch_bounds__(TPB, MINB)
 lmwarp_kernel(const WarpArgs a) {
     constexpr int P = WIN * WIN;
-    static_assert(!COOP || !PFLIB, "the cooperative pass serves the generic-window entry");
+    static_assert(GRP == 1 || !PFLIB, "lane groups serve the generic-window entry");
+    static_assert(GRP == 1 || GRP == 2 || GRP == 4 || GRP == 8, "lanes per window");
+    using LY = WLayout<WIN, GRP>;
+    constexpr int PSTR = LY::PSTR;
     extern __shared__ __align__(16) unsigned char w_smem[];
-    // !COOP: [P][TPB] pixels (FP64) | [28][TPB] | [7][TPB];   COOP: [28][TPB] | [7][TPB] | per warp: chi^2 [32] FP64,
-    // pixel block [32][COOP_PSTR] FP32, accumulator block [32][COOP_ASTR] FP32
-    double* const s_d = reinterpret_cast<double*>(w_smem);
-    float* const s_A = COOP ? reinterpret_cast<float*>(w_smem) : reinterpret_cast<float*>(s_d + P * TPB);   // column-scaled J^T J at the current point
+    // GRP == 1: [P][TPB] pixels | [28][TPB] | [7][TPB];   GRP > 1: [TPB / GRP][PSTR] pixels | [28][TPB] | [7][TPB]
+    PXT* const s_d = reinterpret_cast<PXT*>(w_smem);
+    float* const s_A = reinterpret_cast<float*>(w_smem + LY::template pixel_bytes<TPB, PXT>());   // column-scaled J^T J at the current point
     float* const s_g = s_A + WNT * TPB;                                    // [7][TPB]  column-scaled J^T f
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u;
-    double* const sd = s_d + tid;
+    const int gl = (int)(lane & (unsigned)(GRP - 1));                      // lane within its group
+    const unsigned gbit = 1u << (lane & ~(unsigned)(GRP - 1));             // ballot bit of the group's first lane
+    constexpr unsigned LEADERS = GRP == 1 ? 0xffffffffu : GRP == 2 ? 0x55555555u : GRP == 4 ? 0x11111111u : 0x01010101u;
+    const PXT* const sd = GRP == 1 ? s_d + tid : s_d + (tid / GRP) * PSTR + gl;
     float* const sA = s_A + tid;
     float* const sg = s_g + tid;
-    double* const wss = reinterpret_cast<double*>(s_g + WNP * TPB) + (tid >> 5) * 32;
-    float* const wpx = reinterpret_cast<float*>(reinterpret_cast<double*>(s_g + WNP * TPB) + (TPB / 32) * 32) + (tid >> 5) * (32 * COOP_PSTR);
-    float* const wacc = reinterpret_cast<float*>(reinterpret_cast<double*>(s_g + WNP * TPB) + (TPB / 32) * 32) + (TPB / 32) * (32 * COOP_PSTR)
-                        + (tid >> 5) * (32 * COOP_ASTR);
 
     const float ftol = (float)a.o.ftol, xtol = (float)a.o.xtol, gtol = (float)a.o.gtol, factor = (float)a.o.factor;
     const float machep = (float)WQ_MACHEP;
@@ -529,15 +521,16 @@ lmwarp_kernel(const WarpArgs a) {
         // ------------------------------------------------------------------ refill idle lanes
         __syncwarp();
         if (a.drain_grace > 0 && __any_sync(0xffffffffu, exhausted)) ++drained_ticks;
-        const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+        // (lane groups: the lanes of a group hold identical state, so the ballot has whole groups; one slot per group)
+        const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted) & LEADERS;
         bool fresh = false;                                 // this lane was handed a new window in this tick
         if (want) {
             const int leader = __ffs(want) - 1;
             unsigned long long base = 0;
             if ((int)lane == leader) base = atomicAdd(a.work_counter, (unsigned long long)__popc(want));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if ((want >> lane) & 1u) {
-                const long long slot = (long long)(base + (unsigned long long)__popc(want & ((1u << lane) - 1u)));
+            if (want & gbit) {
+                const long long slot = (long long)(base + (unsigned long long)__popc(want & (gbit - 1u)));
                 if (slot >= n_total) exhausted = true;
                 else {
                     idx = a.resume ? a.strag[slot].idx : slot;
@@ -550,7 +543,7 @@ lmwarp_kernel(const WarpArgs a) {
                         }
 #define WREC(i) ((i) % 4 == 0 ? q[(i) / 4].x : (i) % 4 == 1 ? q[(i) / 4].y : (i) % 4 == 2 ? q[(i) / 4].z : q[(i) / 4].w)
 #pragma unroll
-                        for (int k = 0; k < P; ++k) sd[k * TPB] = (double)(int)WREC(k);
+                        for (int k = 0; k < P; ++k) s_d[k * TPB + tid] = (PXT)(int)WREC(k);
                         cand_h = (int)(WREC(28) >> 16); cand_w = (int)(WREC(28) & 0xffffu);
                         const int4 pre = make_int4((int)WREC(25), (int)WREC(26), (int)WREC(27), 0);
 #undef WREC
@@ -585,10 +578,12 @@ lmwarp_kernel(const WarpArgs a) {
                             bad |= (ql && x[j] < lim.lower(j)) || (qu && x[j] > lim.upper(j)) || (ql && qu && lim.lower(j) >= lim.upper(j));
                         }
                         if (bad) {
+                            if (gl == 0) {
 #pragma unroll
-                            for (int j = 0; j < WNP; ++j) a.params[idx * WNP + j] = x[j];
-                            a.status[idx] = 0; a.niter[idx] = 0; a.nfev[idx] = 0; a.chi2[idx] = -1.0;
-                            if (a.n_damped) a.n_damped[idx] = 0;
+                                for (int j = 0; j < WNP; ++j) a.params[idx * WNP + j] = x[j];
+                                a.status[idx] = 0; a.niter[idx] = 0; a.nfev[idx] = 0; a.chi2[idx] = -1.0;
+                                if (a.n_damped) a.n_damped[idx] = 0;
+                            }
                             active = false;
                         }
                     }
@@ -607,7 +602,7 @@ lmwarp_kernel(const WarpArgs a) {
             // The pixels of every newly claimed window are fetched by the WHOLE warp, coalesced (lane k takes elements
             // k, k + 32, ...): a lane copying its own 121 pixels one after the other kept the other 31 lanes waiting for
             // 121 dependent round trips per refill -- with ~2 refills per warp and tick that was most of the kernel's time
-            unsigned needm = __ballot_sync(0xffffffffu, fresh);
+            unsigned needm = __ballot_sync(0xffffffffu, fresh) & LEADERS;
             while (needm) {
                 const int w = __ffs(needm) - 1;
                 needm &= needm - 1u;
@@ -622,8 +617,8 @@ lmwarp_kernel(const WarpArgs a) {
                 for (int k = 0; k < (P + 31) / 32; ++k) {
                     const int q = k * 32 + (int)lane;
                     if (q < P) {
-                        if (COOP) wpx[w * COOP_PSTR + q] = (float)v[k];
-                        else s_d[q * TPB + (tid & ~31) + w] = v[k];
+                        if (GRP == 1) s_d[q * TPB + (tid & ~31) + w] = (PXT)v[k];
+                        else s_d[(((tid & ~31) + w) / GRP) * PSTR + q] = (PXT)v[k];
                     }
                 }
             }
@@ -634,24 +629,29 @@ lmwarp_kernel(const WarpArgs a) {
             continue;                                                    // (a refill can end at once: status 0)
         }
 
-        if (COOP) {
-            __syncwarp();                                                   // refilled pixel rows are visible to the groups
-            coop_pass<WIN, !PFLIB>(__ballot_sync(0xffffffffu, active), y, wpx, wacc, wss, lane);
+        // -------------------------------------------------------------- pass at the trial point
+        float An[WNT], gn[WNP];
+        double ss = 0.0;
+        if (GRP > 1) {
+            // every lane sums its share of the window's pixels; the butterfly leaves identical totals in the whole group
+            // (idle groups shuffle zeros along: the exchange is warp-wide)
+#pragma unroll
+            for (int i = 0; i < WNT; ++i) An[i] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < WNP; ++i) gn[i] = 0.0f;
+            if (active) g_pass<WIN, GRP, !PFLIB, PXT>(y, sd, gl, An, gn, ss);
+#pragma unroll
+            for (int m = GRP / 2; m >= 1; m >>= 1) {
+                ss += __shfl_xor_sync(0xffffffffu, ss, m);
+#pragma unroll
+                for (int i = 1; i < WNT; ++i) An[i] += __shfl_xor_sync(0xffffffffu, An[i], m);
+#pragma unroll
+                for (int i = 0; i < WNP; ++i) gn[i] += __shfl_xor_sync(0xffffffffu, gn[i], m);
+            }
+            An[0] = (float)P;
         }
         if (active) {
-            // -------------------------------------------------------------- pass at the trial point
-            float An[WNT], gn[WNP];
-            double ss;
-            if (COOP) {
-                An[0] = (float)P;
-#pragma unroll
-                for (int i = 1; i < WNT; ++i) An[i] = wacc[lane * COOP_ASTR + i];
-#pragma unroll
-                for (int i = 0; i < WNP; ++i) gn[i] = wacc[lane * COOP_ASTR + WNT + i];
-                ss = wss[lane];
-            } else {
-                w_pass<WIN, TPB, !PFLIB, PFLIB && WIN == 5 && WRECUR>(y, sd, An, gn, ss);                  // y == x on the first tick of a fit
-            }
+            if (GRP == 1) w_pass<WIN, TPB, !PFLIB, PFLIB && WIN == 5 && WRECUR, PXT>(y, sd, An, gn, ss);      // y == x on the first tick of a fit
             if (mode != MODE_RESUME) ++nfev;
 
             bool have_new = false;
@@ -702,12 +702,14 @@ lmwarp_kernel(const WarpArgs a) {
                 if (status == 0 && accepted &&
                     ((a.cap > 0 && nfev >= a.cap) || (a.drain_grace > 0 && drained_ticks > a.drain_grace))) {
                     // ------------------------------------------------------ park: a long fit leaves the lane
-                    StragRec* rec = a.strag + atomicAdd(a.strag_count, 1ull);
-                    rec->idx = idx;
+                    if (gl == 0) {
+                        StragRec* rec = a.strag + atomicAdd(a.strag_count, 1ull);
+                        rec->idx = idx;
 #pragma unroll
-                    for (int j = 0; j < WNP; ++j) { rec->x[j] = x[j]; rec->diag[j] = diag[j]; }
-                    rec->ss0 = ss0; rec->delta = delta; rec->par = par; rec->xnorm = xnorm;
-                    rec->niter = niter; rec->nfev = nfev; rec->n_damped = n_damped; rec->pad = 0;
+                        for (int j = 0; j < WNP; ++j) { rec->x[j] = x[j]; rec->diag[j] = diag[j]; }
+                        rec->ss0 = ss0; rec->delta = delta; rec->par = par; rec->xnorm = xnorm;
+                        rec->niter = niter; rec->nfev = nfev; rec->n_damped = n_damped; rec->pad = 0;
+                    }
                     active = false;
                 }
             }
@@ -911,7 +913,7 @@ lmwarp_kernel(const WarpArgs a) {
                     o[10] = fmax(ss0, ss1);     // it into rmse / r_2 / sqrt (FP64 sqrt and divisions at full lanes there);
                                                 // o[10] = mpfit .fnorm (:1357-1359)
                     *reinterpret_cast<int4*>(a.out_int + idx * 4) = make_int4(status, niter, nfev, n_damped);
-                } else {
+                } else if (gl == 0) {
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) a.params[idx * WNP + j] = x[j];
                     a.status[idx] = status; a.niter[idx] = niter; a.nfev[idx] = nfev;
@@ -985,29 +987,42 @@ fit_image_generic_kernel(const double* __restrict__ params, const int32_t* __res
 // [64 B header | n start records | n parked-fit records]
 long long warp_scratch_bytes(long long n) { return 64 + (long long)(sizeof(PrepRec) + sizeof(StragRec)) * (n > 0 ? n : 0); }
 
-// Persistent launch(es) of one kernel flavour: phase 1 over every fit (parked after `park_after`
-// passes when that is set), phase 2 over the parked fits.
-template <int WIN, int TPB, int MINB, bool PFLIB, bool COOP = false>
-static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
-    constexpr size_t smem = COOP
-        ? (size_t)(WNT + WNP) * TPB * sizeof(float) + (size_t)(TPB / 32) * (32 * sizeof(double) + 32 * (COOP_PSTR + COOP_ASTR) * sizeof(float))
-        : (size_t)WIN * WIN * TPB * sizeof(double) + (size_t)(WNT + WNP) * TPB * sizeof(float);
-    // function attributes and occupancy are per device: cached per device ordinal (one process may drive several
-    // GPUs from several host threads -- psfio.parallel_image_batch does)
-    static std::atomic<int> per_sm_dev[64];
-    int dev = 0;
-    FSQ_CUDA_CHECK(cudaGetDevice(&dev));
-    int per_sm = (dev >= 0 && dev < 64) ? per_sm_dev[dev].load(std::memory_order_acquire) : 0;
-    if (per_sm == 0) {
-        FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP>, TPB, smem) != cudaSuccess || v < 1) v = 1;
-        per_sm = v;
-        if (dev >= 0 && dev < 64) per_sm_dev[dev].store(v, std::memory_order_release);
+// One instantiation of the LM kernel: shared-memory size, resident blocks per SM (function attributes and occupancy
+// are per device: cached per device ordinal -- one process may drive several GPUs from several host threads,
+// psfio.parallel_image_batch does), launch.
+template <int WIN, int TPB, int MINB, bool PFLIB, int GRP = 1, typename PXT = double>
+struct WKernel {
+    static constexpr int tpb = TPB, grp = GRP;
+    static constexpr size_t smem = WLayout<WIN, GRP>::template smem_bytes<TPB, PXT>();
+    static int per_sm(int* out) {
+        static std::atomic<int> per_sm_dev[64];
+        int dev = 0;
+        FSQ_CUDA_CHECK(cudaGetDevice(&dev));
+        int v = (dev >= 0 && dev < 64) ? per_sm_dev[dev].load(std::memory_order_acquire) : 0;
+        if (v == 0) {
+            FSQ_CUDA_CHECK(cudaFuncSetAttribute(lmwarp_kernel<WIN, TPB, MINB, PFLIB, GRP, PXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, lmwarp_kernel<WIN, TPB, MINB, PFLIB, GRP, PXT>, TPB, smem) != cudaSuccess || v < 1) v = 1;
+            if (dev >= 0 && dev < 64) per_sm_dev[dev].store(v, std::memory_order_release);
+        }
+        *out = v;
+        return FSQ_OK;
     }
+    static int launch(const WarpArgs& a, long long blocks, cudaStream_t st) {
+        lmwarp_kernel<WIN, TPB, MINB, PFLIB, GRP, PXT><<<(unsigned)blocks, TPB, smem, st>>>(a);
+        FSQ_LAUNCH_CHECK();
+        return FSQ_OK;
+    }
+};
+
+// Persistent launch(es): phase 1 (kernel K1) over every fit -- parked after `park_after` passes when that is set --
+// and phase 2 (kernel K2, by default the same) over the parked fits.
+template <typename K1, typename K2 = K1>
+static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
+    int per_sm = 1;
+    { const int rc = K1::per_sm(&per_sm); if (rc != FSQ_OK) return rc; }
     const int use_per_sm = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
     long long blocks = (long long)sm_count() * use_per_sm;
-    const long long need = (a.n + TPB - 1) / TPB;
+    const long long need = (a.n * K1::grp + K1::tpb - 1) / K1::tpb;
     if (need < blocks) blocks = need < 1 ? 1 : need;
     // park_after > 0: park every fit after that many passes; park_after < 0: drain parking -- once the queue is
     // empty, the fits still running -park_after ticks later (the 100+-iteration stragglers) are parked, so that the
@@ -1015,17 +1030,20 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
     // finishes them packed into a few blocks
     const int park = a.o.park_after;
     a.cap = park > 0 ? park : 0; a.drain_grace = park < 0 ? -park : 0; a.resume = 0;
-    lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP><<<(unsigned)blocks, TPB, smem, st>>>(a);
-    FSQ_LAUNCH_CHECK();
+    { const int rc = K1::launch(a, blocks, st); if (rc != FSQ_OK) return rc; }
     if (park != 0) {
         FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
         a.cap = 0; a.drain_grace = 0; a.resume = 1;
-        // the parked fits are few and latency bound: one block per SM leaves the rest of the machine to
-        // whatever the caller has queued on other streams (the next batch's detection and phase 1)
-        const long long want2 = park < 0 ? 16 : sm_count();
-        const long long blocks2 = blocks < want2 ? blocks : want2;
-        lmwarp_kernel<WIN, TPB, MINB, PFLIB, COOP><<<(unsigned)blocks2, TPB, smem, st>>>(a);
-        FSQ_LAUNCH_CHECK();
+        int per_sm2 = 1;
+        { const int rc = K2::per_sm(&per_sm2); if (rc != FSQ_OK) return rc; }
+        // drain parking: the parked fits are few and latency bound -- a few blocks leave the rest of the machine to
+        // whatever the caller has queued on other streams (the next batch's detection and phase 1); parking by pass
+        // count (the 11x11 entry): every parked fit gets its lane group at once
+        long long blocks2 = park < 0 ? 16 : (long long)sm_count() * per_sm2;
+        const long long need2 = (a.n * K2::grp + K2::tpb - 1) / K2::tpb;
+        if (need2 < blocks2) blocks2 = need2 < 1 ? 1 : need2;
+        const int rc = K2::launch(a, blocks2, st);
+        if (rc != FSQ_OK) return rc;
     }
     return FSQ_OK;
 }
@@ -1034,10 +1052,10 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
 // blocks per SM are chosen so that the register budget per thread stays the same (168 registers).
 static int launch_frame_path(WarpArgs& a, unsigned long long* head, cudaStream_t st) {
     switch (a.o.warps_per_sm) {
-        case 1:  return launch_warp<5, 32, 8, true>(a, 1, head, st);
-        case 2:  return launch_warp<5, 64, 4, true>(a, 1, head, st);
-        case 4:  return launch_warp<5, WTHREADS, WMINB, true>(a, 1, head, st);
-        default: return launch_warp<5, WTHREADS, WMINB, true>(a, 0, head, st);
+        case 1:  return launch_warp<WKernel<5, 32, 8, true>>(a, 1, head, st);
+        case 2:  return launch_warp<WKernel<5, 64, 4, true>>(a, 1, head, st);
+        case 4:  return launch_warp<WKernel<5, WTHREADS, WMINB, true>>(a, 1, head, st);
+        default: return launch_warp<WKernel<5, WTHREADS, WMINB, true>>(a, 0, head, st);
     }
 }
 
@@ -1067,6 +1085,34 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     return FSQ_OK;
 }
 
+// 11x11 windows.  Two kernels share the work: the bulk runs one thread per window (the fewest
+// instructions per fit), and every fit still running after W11_PARK passes -- the 5 % that take long, among them the
+// 1-3 % that run to maxiter = 200 (250-330 passes) and set the launch's duration -- is parked and finished by the
+// lane-group kernel, whose ticks are 3x shorter (measured on B200, a warp alone: 26 us per tick with one thread per
+// window, 11.7 us with 4 lanes, 8.3 us with 8 lanes per window).  Which fits are parked depends on their own pass count
+// only, so results do not depend on scheduling.  opts.warps_per_sm selects the other arrangements (cross-checks):
+// -1 thread per window only, -2 / -3 / -4: 4 / 8 / 2 lanes per window for every fit, -5: bulk + 4-lane finish.
+// (Measured and not kept: FP32 pixels in shared memory for 8- / 16-bit window data -- 10 instead of 6 warps per SM for
+//  the thread-per-window kernel at 168 instead of 254 registers: 13.1 instead of 8.9 ms, the tail's ticks get longer;
+//  cutting the batch in two halves on two streams -- persistent grids do not overlap: 10 ms.)
+#ifndef W11_PARK
+#define W11_PARK 32
+#endif
+static int launch_win11(WarpArgs& a, unsigned long long* head, cudaStream_t st) {
+    typedef WKernel<11, 64, 3, false, 1> KT;        // thread per window
+    typedef WKernel<11, 128, 3, false, 4> KG4;
+    typedef WKernel<11, 128, 3, false, 8> KG8;
+    typedef WKernel<11, 128, 3, false, 2> KG2;
+    switch (a.o.warps_per_sm) {
+        case -1: return launch_warp<KT>(a, 0, head, st);
+        case -2: return launch_warp<KG4>(a, 0, head, st);
+        case -3: return launch_warp<KG8>(a, 0, head, st);
+        case -4: return launch_warp<KG2>(a, 0, head, st);
+        case -5: if (a.o.park_after == 0) a.o.park_after = W11_PARK; return launch_warp<KT, KG4>(a, 0, head, st);
+        default: if (a.o.park_after == 0) a.o.park_after = W11_PARK; return launch_warp<KT, KG8>(a, 0, head, st);
+    }
+}
+
 // generic windows (fsq_gaussfit_batch with FSQ_SOLVER_FAST): win = 5 or 11, per-fit start / limits
 int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int win, const double* p0, const double* lo,
                         const double* hi, const uint8_t* lim_lo, const uint8_t* lim_hi, const fsq_lm_opts* opts,
@@ -1077,25 +1123,19 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     a.windows = windows; a.wdtype = dtype_code; a.p0 = p0; a.lo = lo; a.hi = hi; a.lim_lo = lim_lo; a.lim_hi = lim_hi;
     a.n = n; a.o = *opts; a.params = params; a.status = status; a.niter = niter; a.nfev = nfev; a.chi2 = chi2;
     a.n_damped = n_damped;
-    // this entry has no caller-provided scratch: a stream-ordered allocation holds the queue head and,
-    // when parking is requested, the parked states
+    // this entry has no caller-provided scratch: a stream-ordered allocation holds the queue head(s) and the parked states
     fsq_lm_opts o = *opts;
+    a.o = o;
+    const bool need_strag = (o.park_after != 0) || (win == 11);
     void* scratch = nullptr;
-    const size_t bytes = (size_t)(o.park_after != 0 ? 64 + sizeof(StragRec) * (size_t)n : 64);
+    const size_t bytes = 64 + (need_strag ? sizeof(StragRec) * (size_t)n : 0);
     FSQ_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
     unsigned long long* head = (unsigned long long*)scratch;
     a.work_counter = head; a.strag_count = head + 1; a.strag = (StragRec*)((char*)scratch + 64);
     FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, 64, st));
     int rc;
-    a.o = o;
-    if (win == 5) rc = launch_warp<5, 128, 2, false>(a, 0, head, st);
-    // 11x11: thread per window by default.  warps_per_sm == -2 selects the sub-warp variant (cooperative pass, COOP): it
-    // was built to the north_star's "sub-warp per spot" description and measured on B200 -- 2.3x SLOWER on 200 000
-    // windows (21 vs 8.9 ms): with all lanes busy a thread-per-window tick is already lane-efficient (9.3 k warp
-    // instructions per 32 windows), the transposed pass spends 21 k (per-round set-up, 111 shuffles per round, the
-    // serial phase unchanged); it only wins while a warp has a few long fits left.  DESIGN.md section 4.3b.
-    else if (win == 11) rc = (o.warps_per_sm == -2) ? launch_warp<11, 64, 4, false, true>(a, 0, head, st)
-                                                    : launch_warp<11, 64, 3, false>(a, 0, head, st);
+    if (win == 5) rc = launch_warp<WKernel<5, 128, 2, false>>(a, 0, head, st);
+    else if (win == 11) rc = launch_win11(a, head, st);
     else { set_error("the FAST solver takes 5x5 or 11x11 windows (got %d)", win); rc = FSQ_E_ARG; }
     cudaFreeAsync(scratch, st);
     if (rc != FSQ_OK) return rc;

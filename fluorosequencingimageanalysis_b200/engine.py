@@ -209,20 +209,8 @@ def gaussfit_batch(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, want_perr
             return a.to(device=dev, dtype=dt).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
 
-    if isinstance(windows, np.ndarray):
-        if windows.dtype.kind in "iub":
-            w = torch.from_numpy(np.ascontiguousarray(windows.astype(np.int64))).to(dev)
-        else:
-            w = torch.from_numpy(np.ascontiguousarray(windows.astype(np.float64))).to(dev)
-    else:
-        w = windows.to(dev).contiguous()
-        if w.dtype not in (torch.float64, torch.int64):
-            w = w.to(torch.float64 if w.dtype.is_floating_point else torch.int64)
-    if w.dim() == 2:
-        w = w.unsqueeze(0)
+    w = _device_windows(windows, dev)
     n, win, win2 = w.shape
-    if win != win2:
-        raise ValueError("windows must be square")
     p0 = dv(p0, torch.float64).reshape(n, 7)
     lo = dv(lo, torch.float64).reshape(n, 7)
     hi = dv(hi, torch.float64).reshape(n, 7)
@@ -291,15 +279,25 @@ def gaussfit_batch_trace(windows, p0, lo, hi, lim_lo, lim_hi, faithful=True, tra
     return r, trace.cpu().numpy()
 
 
+_NP_WINDOW_DTYPES = (np.uint8, np.uint16, np.int16, np.int32, np.int64, np.float64)
+
+
 def _device_windows(windows, dev):
-    """numpy / torch windows -> contiguous CUDA tensor [n,win,win], int64 for integer pixels, float64 otherwise"""
+    """numpy / torch windows -> contiguous CUDA tensor [n,win,win]: camera integers (uint8 / uint16 / int16 / int32 /
+    int64) and float64 keep their type -- the kernels read all six, and the 11x11 FAST kernels hold 8- / 16-bit pixels
+    in shared memory as FP32 (exact), which doubles their occupancy -- anything else becomes int64 or float64"""
     if isinstance(windows, np.ndarray):
         a = windows
-        kind = np.int64 if a.dtype.kind in "iub" else np.float64
-        w = torch.from_numpy(np.ascontiguousarray(a.astype(kind))).to(dev)
+        if a.dtype not in _NP_WINDOW_DTYPES or (a.dtype == np.uint16 and not hasattr(torch, "uint16")):
+            a = a.astype(np.int64 if a.dtype.kind in "iub" else np.float64)
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.uint16:
+            w = torch.from_numpy(a.view(np.int16)).view(torch.uint16).to(dev)
+        else:
+            w = torch.from_numpy(a).to(dev)
     else:
         w = windows.to(dev).contiguous()
-        if w.dtype not in (torch.float64, torch.int64):
+        if w.dtype not in _TORCH_DTYPE_CODE:
             w = w.to(torch.float64 if w.dtype.is_floating_point else torch.int64)
     if w.dim() == 2:
         w = w.unsqueeze(0)

@@ -351,10 +351,13 @@ def test_config3_experiment_stack_is_frame_independent():
     assert off == int(batch.n_cand[-1])
 
 
-def test_fast_11x11_sub_warp_variant_matches_the_reference_too():
-    """fsq_lm_opts.warps_per_sm = -2: the 11x11 kernel with the cooperative pass (8 lanes per window, shuffle reductions,
-    FP32 pixel block) -- same algorithm as the thread-per-window kernel, different summation order: same figures against
-    the reference on both 11x11 golden sets, and the same answer as the default kernel wherever the fit is not chaotic."""
+def test_fast_11x11_lane_group_kernels_match_the_reference_too():
+    """The arrangements of the 11x11 FAST kernel (fsq_lm_opts.warps_per_sm): 0 = the default, a thread-per-window bulk whose
+    fits are parked after 32 passes and finished by the 8-lanes-per-window kernel; -1 = thread per window only; -2 / -3 /
+    -4 = 4 / 8 / 2 lanes per window for every fit (pass split over the lanes, xor-butterfly sums); -5 = bulk + 4-lane
+    finish.  Same algorithm, different summation order in the lane-group passes: the same figures against the reference
+    on both 11x11 golden sets, the same answer as the thread-per-window kernel wherever the fit is not chaotic, and --
+    default arrangement -- bit-identical results for every fit that ends before it would be parked."""
     engine, _, _, _lib = _mods()
     for name in ("seed0", "d2048"):
         g = golden("fits11_%s.npz" % name)
@@ -362,19 +365,32 @@ def test_fast_11x11_sub_warp_variant_matches_the_reference_too():
         lo, hi, lmin, lmax = engine.GAUSSFIT_DEFAULT_LIMITS
         t = lambda v: np.tile(v, (n, 1))
         out = {}
-        for tag, wps in (("thread", 0), ("coop", -2)):
+        for tag, wps in (("thread", -1), ("default", 0), ("g4", -2), ("g8", -3), ("g2", -4), ("bulk+g4", -5)):
             o = _lib.default_opts(faithful=False, solver="fast", warps_per_sm=wps)
             r = engine.gaussfit_batch(g["windows"], g["p0"], t(lo), t(hi), t(lmin), t(lmax), solver="fast", opts=o, rescue=False)
-            out[tag] = (r.params.cpu().numpy(), r.status.cpu().numpy(), r.chi2.cpu().numpy())
+            out[tag] = (r.params.cpu().numpy(), r.status.cpu().numpy(), r.chi2.cpu().numpy(), r.nfev.cpu().numpy())
         robust = g["n_qrsolv"] == 0
-        P, s, chi = out["coop"]
-        ok = agree(P, g["ref_params"]) & (s > 0) & (g["ref_status"] > 0)
-        same = agree(P, out["thread"][0])
-        print("fast 11x11 sub-warp [%s]: robust-set agreement %.4f (n=%d), chi2 not worse than the reference %.4f, equal to the "
-              "thread-per-window kernel %.4f" % (name, ok[robust].mean(), robust.sum(), (chi <= g["ref_fnorm"] * (1 + 1e-6)).mean(), same.mean()))
-        assert ok[robust].mean() >= 0.99 and (s > 0).all()
-        assert (chi <= g["ref_fnorm"] * (1 + 1e-6)).mean() >= 0.97
-        assert same[robust].mean() >= 0.99
+        for tag in ("default", "g4", "g8", "g2", "bulk+g4"):
+            P, s, chi, nfev = out[tag]
+            ok = agree(P, g["ref_params"]) & (s > 0) & (g["ref_status"] > 0)
+            same = agree(P, out["thread"][0])
+            print("fast 11x11 %-8s [%s]: robust-set agreement %.4f (n=%d), chi2 not worse than the reference %.4f, equal to the "
+                  "thread-per-window kernel %.4f" % (tag, name, ok[robust].mean(), robust.sum(), (chi <= g["ref_fnorm"] * (1 + 1e-6)).mean(), same.mean()))
+            assert ok[robust].mean() >= 0.99 and (s > 0).all()
+            assert (chi <= g["ref_fnorm"] * (1 + 1e-6)).mean() >= 0.97
+            assert same[robust].mean() >= 0.99
+        # the default arrangement only changes the fits it parks (those with more than 32 passes)
+        Pt, st, chit, nft = out["thread"]
+        Pd, sd, chid, nfd = out["default"]
+        short = nft < 32
+        assert short.sum() > 0.8 * n
+        assert np.array_equal(Pt[short].view(np.int64), Pd[short].view(np.int64)) and np.array_equal(st[short], sd[short])
+        assert np.array_equal(chit[short].view(np.int64), chid[short].view(np.int64)) and np.array_equal(nft[short], nfd[short])
+        # narrow integer windows are read as they are (no host-side widening): same fits as the float64 copy
+        if np.all(g["windows"] == np.round(g["windows"])) and g["windows"].min() >= 0 and g["windows"].max() < 65536:
+            o = _lib.default_opts(faithful=False, solver="fast")
+            r16 = engine.gaussfit_batch(g["windows"].astype(np.uint16), g["p0"], t(lo), t(hi), t(lmin), t(lmax), solver="fast", opts=o, rescue=False)
+            assert np.array_equal(r16.params.cpu().numpy().view(np.int64), Pd.view(np.int64))
 
 
 def test_field_stream_partial_batches_equal_single_calls():
