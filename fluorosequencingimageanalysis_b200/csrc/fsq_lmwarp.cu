@@ -76,9 +76,11 @@ struct WarpArgs {
 // scattered pixels) -- the refill was 10 % of the kernel's time with 2 lanes of every warp refilling per tick.
 struct __align__(16) PrepRec {
     int px[25];                  // the 5x5 raw window, raster order
-    int med, max, sum;           // numpy.median / max / sum of the window (pflib.py:199-205)
+    int med, max;                // numpy.median / max of the window (pflib.py:199-200)
     unsigned hw;                 // candidate pixel: h << 16 | w
     double sst;                  // total sum of squares around the window mean (r_2, pflib.py:464)
+    double lo1;                  // amplitude floor (max - mean) / 3 (pflib.py:205): two FP64 divisions that the fully
+                                 // parallel start-record kernel does, not the two refilling lanes of an LM warp
 };
 static_assert(sizeof(PrepRec) == 128, "PrepRec must be 128 bytes");
 
@@ -173,9 +175,10 @@ fit_prep_kernel(const WarpArgs a) {
     for (int r = 0; r < 5; ++r)
 #pragma unroll
         for (int c = 0; c < 5; ++c) rec.px[r * 5 + c] = w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
-    rec.med = imed; rec.max = imax; rec.sum = (int)isum;
+    rec.med = imed; rec.max = imax;
     rec.hw = ((unsigned)ch << 16) | (unsigned)cw;
     rec.sst = sst;
+    rec.lo1 = ((double)imax - (double)(int)isum / 25.0) / 3.0;                                // pflib.py:205
     uint4* dst = reinterpret_cast<uint4*>(a.prep + i);
     const uint4* src = reinterpret_cast<const uint4*>(&rec);
 #pragma unroll
@@ -612,12 +615,10 @@ lmwarp_kernel(const WarpArgs a) {
 #define WREC(i) ((i) % 4 == 0 ? q[(i) / 4].x : (i) % 4 == 1 ? q[(i) / 4].y : (i) % 4 == 2 ? q[(i) / 4].z : q[(i) / 4].w)
 #pragma unroll
                         for (int k = 0; k < P; ++k) s_d[k * TPB + tid] = (PXT)(int)WREC(k);
-                        cand_h = (int)(WREC(28) >> 16); cand_w = (int)(WREC(28) & 0xffffu);
-                        const int4 pre = make_int4((int)WREC(25), (int)WREC(26), (int)WREC(27), 0);
+                        cand_h = (int)(WREC(27) >> 16); cand_w = (int)(WREC(27) & 0xffffu);
+                        lim.lo1 = __hiloint2double((int)WREC(31), (int)WREC(30));          // pflib.py:205 (fit_prep_kernel)
+                        x[0] = (double)(int)WREC(25); x[1] = (double)(int)WREC(26); x[2] = 2.5; x[3] = 2.5; x[4] = 1.0; x[5] = 1.0; x[6] = 0.0;
 #undef WREC
-                        const double dmax = (double)pre.y, dmean = (double)pre.z / 25.0;
-                        lim.lo1 = (dmax - dmean) / 3.0;                                    // pflib.py:205
-                        x[0] = (double)pre.x; x[1] = dmax; x[2] = 2.5; x[3] = 2.5; x[4] = 1.0; x[5] = 1.0; x[6] = 0.0;
 #pragma unroll
                         for (int j = 0; j < WNP; ++j) {                                    // gaussfitter.py:202-204
                             if (lim.has_hi(j) && x[j] > lim.upper(j)) x[j] = lim.upper(j);
@@ -795,10 +796,11 @@ lmwarp_kernel(const WarpArgs a) {
                 float gmax = 0.0f;
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) {
-                    const bool lp = lim.has_lo(j) && (x[j] == lim.lower(j));
-                    const bool up = lim.has_hi(j) && (x[j] == lim.upper(j));
+                    // (bitwise & and |: no short-circuit branches in the serial chain -- every operand is cheap and side-effect free)
+                    const bool lp = lim.has_lo(j) & (x[j] == lim.lower(j));
+                    const bool up = lim.has_hi(j) & (x[j] == lim.upper(j));
                     lpeg |= (lp ? 1u : 0u) << j; upeg |= (up ? 1u : 0u) << j;
-                    const bool zero = (lp && gn[j] > 0.0f) || (up && gn[j] < 0.0f);
+                    const bool zero = (lp & (gn[j] > 0.0f)) | (up & (gn[j] < 0.0f));
                     gn[j] = zero ? gn[j] * 0.0f : gn[j];
                     const float ajj = zero ? An[wtri(j, j)] * 0.0f : An[wtri(j, j)];
                     const float rs = ajj > 0.0f ? rsqrtf(ajj) : 0.0f;
@@ -912,9 +914,18 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
                 for (int j = 0; j < WNP; ++j) {
                     const double xn = x[j] + (double)pf[j];
-                    if (fabsf(pf[j]) > machep) {
-                        if (lim.has_lo(j) && xn < lim.lower(j)) alpha = fminf(alpha, __fdividef((float)(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
-                        if (lim.has_hi(j) && xn > lim.upper(j)) alpha = fminf(alpha, __fdividef((float)(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                    // branch-free: a step hits at most one of a parameter's two bounds, so one division per parameter serves
+                    // both tests (twelve short branches with a MUFU each used to sit in this chain)
+                    const bool big = fabsf(pf[j]) > machep;
+                    const bool vlo = big & lim.has_lo(j) & (xn < lim.lower(j));
+                    const bool vhi = big & lim.has_hi(j) & (xn > lim.upper(j));
+                    if (PFLIB) {
+                        const double bnd = vlo ? lim.lower(j) : lim.upper(j);
+                        const float r = __fdividef((float)(bnd - x[j]), pf[j]) * (1.0f + 4e-7f);
+                        alpha = (vlo | vhi) ? fminf(alpha, r) : alpha;
+                    } else {
+                        if (vlo) alpha = fminf(alpha, __fdividef((float)(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (vhi) alpha = fminf(alpha, __fdividef((float)(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
                     }
                 }
                 float pn = 0.0f;
