@@ -186,6 +186,16 @@ fit_prep_kernel(const WarpArgs a) {
     a.out_fit[i * 12 + 9] = s_n;                                          // illumina_s_n, pflib.py:261-281 (final)
 }
 
+// double -> float, round to nearest.  The file is compiled with -ftz=true, under which a plain (float) cast becomes
+// cvt.rn.ftz.f32.f64 -- emulated in SASS by an FP64 compare and a multiply around every conversion (56 of them in the tick,
+// ten per pixel row of the pass).  The non-flushing form is one F2F; a denormal result is flushed by the FP32 operation that
+// consumes it.
+__device__ __forceinline__ float d2f(double v) {
+    float r;
+    asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(v));
+    return r;
+}
+
 // -------------------------------------------------------------------------------------------
 // Branch-free FP64 helpers of the pass.  exp: Cody-Waite reduction by ln2 + degree-12 Taylor
 // polynomial (|r| <= ln2/2: 2 ulp, measured against numpy.exp), argument <= 0 and bounded by the
@@ -328,7 +338,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
             const double dy = pt[2] - (double)c;
             const double cav = dy * sxs, cbv = dy * cys;
             if (!RECUR) { ca[c] = cav; cb[c] = cbv; }
-            caf[c] = (float)cav; cbf[c] = (float)cbv;
+            caf[c] = d2f(cav); cbf[c] = d2f(cbv);
         }
     }
     double Er = 0.0, Grow = 0.0, Grr = 0.0, Kc = 0.0, Kr = 0.0, Kx = 0.0;
@@ -343,10 +353,10 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
         Kr = w_exp_neg<false>(-qr);
         Kx = w_exp_neg<false>(qx);
     }
-    const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
-    const float iwxf = (float)iwx, iwyf = (float)iwy;
-    const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
-    const float cyf = (float)pt[2];
+    const float Af = d2f(Aa), sx = d2f(sxs), cxw = d2f(cxs), sy = d2f(sys), cyw = d2f(cys);
+    const float iwxf = d2f(iwx), iwyf = d2f(iwy);
+    const float krot = d2f((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
+    const float cyf = d2f(pt[2]);
 #pragma unroll
     for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
 #pragma unroll
@@ -364,7 +374,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
 #endif
     for (int r = 0; r < WIN; ++r) {
         const double ra = dx * cxs, rb = dx * sys;
-        const float raf = (float)ra, rbf = (float)rb;
+        const float raf = d2f(ra), rbf = d2f(rb);
         const PXT* drow = sd + r * WIN * TPB;
         dx -= 1.0;
         double Ec = Er, Gc = Grow;
@@ -395,7 +405,7 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
             else E = CLAMP ? ezero * w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av)) : w_exp_neg<CLAMP>(-0.5 * fma(bv, bv, av * av));
             const double f = (double)drow[c * TPB] - fma(Aa, E, Hh);
             ss = fma(f, f, ss);
-            const float Ef = (float)E, ff = (float)f;
+            const float Ef = d2f(E), ff = d2f(f);
             const float AE = Af * Ef;
             const float AEa = AE * af, AEb = AE * bf;
             float j[WNP];
@@ -453,9 +463,9 @@ __device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __res
     const double cxs = cs * iwx, sxs = sn * iwx, cys = cs * iwy, sys = sn * iwy;
     // a(r, c) = (p3 - r) cxs - (p2 - c) sxs,  b(r, c) = (p3 - r) sys + (p2 - c) cys
     const double a00 = fma(pt[3], cxs, -pt[2] * sxs), b00 = fma(pt[3], sys, pt[2] * cys);
-    const float Af = (float)Aa, sx = (float)sxs, cxw = (float)cxs, sy = (float)sys, cyw = (float)cys;
-    const float iwxf = (float)iwx, iwyf = (float)iwy;
-    const float krot = (float)((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
+    const float Af = d2f(Aa), sx = d2f(sxs), cxw = d2f(cxs), sy = d2f(sys), cyw = d2f(cys);
+    const float iwxf = d2f(iwx), iwyf = d2f(iwy);
+    const float krot = d2f((pt[5] * iwx - pt[4] * iwy) * WQ_DEG2RAD);
 #pragma unroll
     for (int i = 0; i < WNT; ++i) A[i] = 0.0f;
 #pragma unroll
@@ -481,8 +491,8 @@ __device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __res
         const double d = ok ? (double)px[sl * G] : Hh;              // beyond the window: zero residual, zero Jacobian
         const double f = d - fma(Aa, E, Hh);
         ss = fma(f, f, ss);
-        const float af = (float)av, bf = (float)bv;
-        const float Ef = (float)E, ff = (float)f;
+        const float af = d2f(av), bf = d2f(bv);
+        const float Ef = d2f(E), ff = d2f(f);
         const float AE = Af * Ef;
         const float AEa = AE * af, AEb = AE * bf;
         float j[WNP];
@@ -733,7 +743,7 @@ lmwarp_kernel(const WarpArgs a) {
                 // ---------------------------------------------------------- trial bookkeeping (:1245-1335)
                 ss1 = ss;
                 float actred = -1.0f;
-                if (0.01 * ss1 < ss0) actred = (float)(ss0 - ss1) * rss0;               // 1 - (fnorm1/fnorm)^2
+                if (0.01 * ss1 < ss0) actred = d2f(ss0 - ss1) * rss0;               // 1 - (fnorm1/fnorm)^2
                 float ratio = 0.0f;
                 if (prered != 0.0f) ratio = __fdividef(actred, prered);
                 if (ratio <= 0.25f) {                                                    // :1276-1288
@@ -751,7 +761,7 @@ lmwarp_kernel(const WarpArgs a) {
                 if (accepted) {
                     float s = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < WNP; ++j) { x[j] = y[j]; const float t = diag[j] * (float)x[j]; s = fmaf(t, t, s); }
+                    for (int j = 0; j < WNP; ++j) { x[j] = y[j]; const float t = diag[j] * d2f(x[j]); s = fmaf(t, t, s); }
                     xnorm = sqrtf(s);
                     ss0 = ss1;
                     ++niter;
@@ -787,7 +797,7 @@ lmwarp_kernel(const WarpArgs a) {
                 // parked
             } else if (status == 0 && have_new) {
                 // ---------------------------------------------------------- new linearisation at x
-                rss0 = __fdividef(1.0f, (float)ss0);
+                rss0 = __fdividef(1.0f, d2f(ss0));
                 // pegged parameters: zero the column when the gradient pushes outwards (:1073-1091)
                 // (a zeroed column is not multiplied out of the 28 accumulators: its diagonal is read as 0 here and
                 //  its scale factor as 0 in the store below, which leaves the same numbers in shared memory)
@@ -816,7 +826,7 @@ lmwarp_kernel(const WarpArgs a) {
 #pragma unroll
                     for (int j = 0; j < WNP; ++j) {
                         diag[j] = (acn[j] == 0.0f) ? 1.0f : acn[j];
-                        const float t = diag[j] * (float)x[j];
+                        const float t = diag[j] * d2f(x[j]);
                         s = fmaf(t, t, s);
                     }
                     xnorm = sqrtf(s);
@@ -921,11 +931,11 @@ lmwarp_kernel(const WarpArgs a) {
                     const bool vhi = big & lim.has_hi(j) & (xn > lim.upper(j));
                     if (PFLIB) {
                         const double bnd = vlo ? lim.lower(j) : lim.upper(j);
-                        const float r = __fdividef((float)(bnd - x[j]), pf[j]) * (1.0f + 4e-7f);
+                        const float r = __fdividef(d2f(bnd - x[j]), pf[j]) * (1.0f + 4e-7f);
                         alpha = (vlo | vhi) ? fminf(alpha, r) : alpha;
                     } else {
-                        if (vlo) alpha = fminf(alpha, __fdividef((float)(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
-                        if (vhi) alpha = fminf(alpha, __fdividef((float)(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (vlo) alpha = fminf(alpha, __fdividef(d2f(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
+                        if (vhi) alpha = fminf(alpha, __fdividef(d2f(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
                     }
                 }
                 float pn = 0.0f;
