@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # the source (two template instantiations give bit-identical fits) -- DESIGN.md "Parity".
 # The FAST LM kernel's FP32 half (Jacobian, normal equations, Cholesky, lmpar: quantities that only shape the step) is
 # compiled with flush-to-zero and the approximate square root: the IEEE square-root fix-up and the denormal paths of
-# rsqrt / reciprocal sit in the serial chains of every tick.  Measured on B200 (profiles/r02c_lm_ffma2_ab.txt): 4.43 ->
+# rsqrt / reciprocal sit in the serial chains of every tick.  Measured on B200 (profiles/r02d_lm_ab.txt): 4.43 ->
 # 4.01 ms per 200-frame launch with three in flight, same iteration counts, same parity figures.  Its FP64 half (residual,
 # chi^2, parameters, bounds) is not touched by these flags.
 EXTRA_FLAGS = {"fsq_lmfit.cu": ["-fmad=false"], "fsq_lmwarp.cu": ["-ftz=true", "-prec-sqrt=false"]}
