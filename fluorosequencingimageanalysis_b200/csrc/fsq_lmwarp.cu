@@ -61,6 +61,7 @@ struct WarpArgs {
     double* params; int32_t* status; int32_t* niter; int32_t* nfev; double* chi2; int32_t* n_damped;
     long long n; const long long* n_dev;
     fsq_lm_opts o;
+    float ftol_f, xtol_f, gtol_f, factor_f;   // the tolerances of o as FP32 (converted once on the host: a conversion in the kernel is re-done every tick)
     double* out_fit; int32_t* out_int; double* fit_img;
     unsigned long long* work_counter;        // queue head of the running launch
     unsigned long long* strag_count;         // number of parked fits (phase 1 appends, phase 2 consumes)
@@ -543,7 +544,9 @@ struct WLayout {
         return GRP == 1 ? (size_t)P * TPB * sizeof(PXT) : (((size_t)(TPB / GRP) * PSTR * sizeof(PXT) + 15) / 16) * 16;
     }
     template <int TPB, typename PXT>
-    __host__ __device__ static constexpr size_t smem_bytes() { return pixel_bytes<TPB, PXT>() + (size_t)(WNT + WNP) * TPB * sizeof(float); }
+    __host__ __device__ static constexpr size_t smem_bytes() {
+        return pixel_bytes<TPB, PXT>() + (size_t)(WNT + WNP) * TPB * sizeof(float) + (GRP > 1 ? (size_t)(TPB / GRP) * 14 * sizeof(double) : 0);
+    }
 };
 
 template <int WIN, int TPB, int MINB, bool PFLIB, int GRP = 1, typename PXT = double>
@@ -555,7 +558,7 @@ lmwarp_kernel(const WarpArgs a) {
     using LY = WLayout<WIN, GRP>;
     constexpr int PSTR = LY::PSTR;
     extern __shared__ __align__(16) unsigned char w_smem[];
-    // GRP == 1: [P][TPB] pixels | [28][TPB] | [7][TPB];   GRP > 1: [TPB / GRP][PSTR] pixels | [28][TPB] | [7][TPB]
+    // GRP == 1: [P][TPB] pixels | [28][TPB] | [7][TPB];   GRP > 1: [TPB / GRP][PSTR] pixels | [28][TPB] | [7][TPB] | [TPB / GRP][14] limits
     PXT* const s_d = reinterpret_cast<PXT*>(w_smem);
     float* const s_A = reinterpret_cast<float*>(w_smem + LY::template pixel_bytes<TPB, PXT>());   // column-scaled J^T J at the current point
     float* const s_g = s_A + WNT * TPB;                                    // [7][TPB]  column-scaled J^T f
@@ -567,8 +570,11 @@ lmwarp_kernel(const WarpArgs a) {
     const PXT* const sd = GRP == 1 ? s_d + tid : s_d + (tid / GRP) * PSTR + gl;
     float* const sA = s_A + tid;
     float* const sg = s_g + tid;
+    // lane groups: the window's box limits (lower[7] | upper[7]) -- the serial phase reads them twice per tick, and from
+    // global memory that is fourteen dependent round trips in the chain that sets the length of a long fit's tick
+    double* const s_lim = reinterpret_cast<double*>(s_g + WNP * TPB) + (GRP > 1 ? (tid / GRP) * 14 : 0);
 
-    const float ftol = (float)a.o.ftol, xtol = (float)a.o.xtol, gtol = (float)a.o.gtol, factor = (float)a.o.factor;
+    const float ftol = a.ftol_f, xtol = a.xtol_f, gtol = a.gtol_f, factor = a.factor_f;
     const float machep = (float)WQ_MACHEP;
     const int maxiter = a.o.maxiter;
     long long n_total = a.n;
@@ -637,7 +643,10 @@ lmwarp_kernel(const WarpArgs a) {
                         }
                     } else {
                         fresh = true;                                  // pixels: loaded by the whole warp below
-                        lim.lo = a.lo + idx * WNP; lim.hi = a.hi + idx * WNP;
+                        if (GRP > 1) {
+                            for (int k = gl; k < 14; k += GRP) s_lim[k] = (k < WNP) ? a.lo[idx * WNP + k] : a.hi[idx * WNP + k - WNP];
+                            lim.lo = s_lim; lim.hi = s_lim + WNP;       // (visible to the group after the __syncwarp below)
+                        } else { lim.lo = a.lo + idx * WNP; lim.hi = a.hi + idx * WNP; }
                         lim.qll = 0; lim.qul = 0;
 #pragma unroll
                         for (int j = 0; j < WNP; ++j) {
@@ -650,11 +659,14 @@ lmwarp_kernel(const WarpArgs a) {
                     ss0 = -1.0; ss1 = -1.0; par = 0.0f; nonfinite = false;
                     if (!PFLIB) {
                         // mpfit.py:956-964: start outside the limits / inconsistent limits -> status 0, nothing runs
+                        // (the limits come from global memory here: a lane group's shared copy is being written)
                         bool bad = false;
+                        const double* glo = a.lo + idx * WNP;
+                        const double* ghi = a.hi + idx * WNP;
 #pragma unroll
                         for (int j = 0; j < WNP; ++j) {
                             const bool ql = lim.has_lo(j), qu = lim.has_hi(j);
-                            bad |= (ql && x[j] < lim.lower(j)) || (qu && x[j] > lim.upper(j)) || (ql && qu && lim.lower(j) >= lim.upper(j));
+                            bad |= (ql && x[j] < glo[j]) || (qu && x[j] > ghi[j]) || (ql && qu && glo[j] >= ghi[j]);
                         }
                         if (bad) {
                             if (gl == 0) {
@@ -929,13 +941,10 @@ lmwarp_kernel(const WarpArgs a) {
                     const bool big = fabsf(pf[j]) > machep;
                     const bool vlo = big & lim.has_lo(j) & (xn < lim.lower(j));
                     const bool vhi = big & lim.has_hi(j) & (xn > lim.upper(j));
-                    if (PFLIB) {
+                    {
                         const double bnd = vlo ? lim.lower(j) : lim.upper(j);
                         const float r = __fdividef(d2f(bnd - x[j]), pf[j]) * (1.0f + 4e-7f);
                         alpha = (vlo | vhi) ? fminf(alpha, r) : alpha;
-                    } else {
-                        if (vlo) alpha = fminf(alpha, __fdividef(d2f(lim.lower(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
-                        if (vhi) alpha = fminf(alpha, __fdividef(d2f(lim.upper(j) - x[j]), pf[j]) * (1.0f + 4e-7f));
                     }
                 }
                 float pn = 0.0f;
@@ -1154,7 +1163,7 @@ int warp_fit_candidates(const void* frames, int dtype_code, int H, int W, const 
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.frames = frames; a.fdtype = dtype_code; a.H = H; a.W = W; a.cand_hw = cand_hw; a.cand_frame = cand_frame;
-    a.n = n; a.n_dev = n_dev; a.o = *opts; a.out_fit = out_fit; a.out_int = out_int; a.fit_img = fit_img;
+    a.n = n; a.n_dev = n_dev; a.o = *opts; a.ftol_f = (float)opts->ftol; a.xtol_f = (float)opts->xtol; a.gtol_f = (float)opts->gtol; a.factor_f = (float)opts->factor; a.out_fit = out_fit; a.out_int = out_int; a.fit_img = fit_img;
     unsigned long long* head = (unsigned long long*)scratch;          // [0] queue head, [1] parked count
     a.work_counter = head; a.strag_count = head + 1;
     a.prep = (PrepRec*)((char*)scratch + 64);
@@ -1210,7 +1219,7 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     WarpArgs a;
     memset(&a, 0, sizeof(a));
     a.windows = windows; a.wdtype = dtype_code; a.p0 = p0; a.lo = lo; a.hi = hi; a.lim_lo = lim_lo; a.lim_hi = lim_hi;
-    a.n = n; a.o = *opts; a.params = params; a.status = status; a.niter = niter; a.nfev = nfev; a.chi2 = chi2;
+    a.n = n; a.o = *opts; a.ftol_f = (float)opts->ftol; a.xtol_f = (float)opts->xtol; a.gtol_f = (float)opts->gtol; a.factor_f = (float)opts->factor; a.params = params; a.status = status; a.niter = niter; a.nfev = nfev; a.chi2 = chi2;
     a.n_damped = n_damped;
     // this entry has no caller-provided scratch: a stream-ordered allocation holds the queue head(s) and the parked states
     fsq_lm_opts o = *opts;
