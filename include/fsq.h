@@ -112,10 +112,12 @@ typedef struct fsq_lm_opts {
                            flight (engine.FieldStream) each thread then works through many more fits, so
                            far fewer warp-ticks are spent on half-empty warps waiting for their last long
                            fit, and one batch's tail runs underneath the other batches' bulk.
-                           -2 (fsq_gaussfit_batch, 11x11 windows only): the sub-warp variant of the 11x11 kernel
-                           (8 lanes per window in the pass, shuffle reductions) instead of one thread per window;
-                           same algorithm, different summation order; measured slower, kept as a
-                           cross-check.                                                               */
+                           fsq_gaussfit_batch, 11x11 windows: 0 = a thread-per-window launch whose
+                           fits are parked after park_after passes (default 32) and finished by the kernel with 8
+                           lanes per window (pass split over the lanes, shuffle reductions); -1 = thread per window
+                           only; -2 / -3 / -4 = 4 / 8 / 2 lanes per window for every fit; -5 = thread-per-window launch
+                           + 4-lane finish.  Same algorithm, different summation order in the lane-group passes: fits
+                           that end before they are parked are bit-identical in every arrangement.          */
 } fsq_lm_opts;
 
 /* Solvers behind the two fit entry points.
