@@ -370,3 +370,30 @@ def test_median_pair_network_is_a_pair_of_medians_and_the_header_is_current():
     assert (n_raw, n_sorted) == (216, 108)
     committed = open(os.path.join(ROOT, "fluorosequencingimageanalysis_b200", "csrc", "fsq_median_pair.cuh")).read()
     assert committed == text
+
+
+def test_window_batches_keep_camera_integer_types():
+    """engine._device_windows: 8- / 16- / 32- / 64-bit camera integers and float64 reach the kernels as they are (a 200 000
+    window batch of uint16 pixels is 48 MB, not 194 MB, on its way to the device); anything else is widened to int64 /
+    float64; a single window becomes a batch of one; non-square windows raise like the reference's 5x5 assert."""
+    import numpy as np
+    import torch
+    from fluorosequencingimageanalysis_b200 import engine
+    cpu = torch.device("cpu")
+    w = (np.arange(2 * 11 * 11) % 4096).reshape(2, 11, 11)
+    for dt, want in ((np.uint8, torch.uint8), (np.int16, torch.int16), (np.int32, torch.int32), (np.int64, torch.int64),
+                     (np.float64, torch.float64), (np.float32, torch.float64), (np.uint32, torch.int64), (np.bool_, torch.int64)):
+        t = engine._device_windows((w % 200).astype(dt) if dt in (np.uint8, np.bool_) else w.astype(dt), cpu)
+        assert t.dtype == want and tuple(t.shape) == (2, 11, 11) and t.is_contiguous(), (dt, t.dtype)
+    if hasattr(torch, "uint16"):
+        t = engine._device_windows(w.astype(np.uint16), cpu)
+        assert t.dtype == torch.uint16 and np.array_equal(t.view(torch.int16).numpy().view(np.uint16), w.astype(np.uint16))
+    assert tuple(engine._device_windows(w[0].astype(np.float64), cpu).shape) == (1, 11, 11)
+    t = engine._device_windows(torch.from_numpy(w.astype(np.float32)), cpu)
+    assert t.dtype == torch.float64
+    try:
+        engine._device_windows(np.zeros((3, 5, 7)), cpu)
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("non-square windows must raise")
