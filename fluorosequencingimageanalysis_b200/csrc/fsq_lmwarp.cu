@@ -169,13 +169,11 @@ fit_prep_kernel(const WarpArgs a) {
         sst = __dadd_rn(sst, __dmul_rn(e, e));
     }
     const double s_n = illumina_sn<5>(5, [&](int r, int c) { return (long long)v[r * 5 + c]; });   // bit-identical to pflib.illumina_s_n
-    const int imed = median25<int>(v);                           // numpy.median of 25 (pflib.py:199)
-    // (v[] is permuted by the selection network: re-read the window for the record)
+    // (the selection network permutes its input: the record keeps the window, the network gets a copy)
     PrepRec rec;
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) rec.px[r * 5 + c] = w_ld_int(a.frames, a.fdtype, fbase + (size_t)r * a.W + c);
+    for (int q = 0; q < 25; ++q) rec.px[q] = v[q];
+    const int imed = median25<int>(v);                           // numpy.median of 25 (pflib.py:199)
     rec.med = imed; rec.max = imax;
     rec.hw = ((unsigned)ch << 16) | (unsigned)cw;
     rec.sst = sst;
