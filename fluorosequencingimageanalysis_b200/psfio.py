@@ -252,13 +252,37 @@ def image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None
     return processed
 
 
-def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None, num_processes=None):
-    """pflib.py:1000-1111 with GPUs in place of worker processes: images are balanced over
-    ``num_processes`` partitions by candidate count exactly like the reference (detection runs once
-    on the first device for the count), each partition runs ``image_batch`` on its own GPU
-    (partition k -> device k mod device_count) in its own host thread.  No collective."""
+#: how parallel_image_batch runs its partitions: "thread" = host threads of this process, one per partition, each bound
+#: to its GPU; "process" = one worker process per partition (multiprocessing, spawn context), the reference's arrangement
+#: (multiprocessing.Pool, pflib.py:1082).  Measured on a B200 box (16 host cores, one GPU, tools/gpu_io_bench.py, 384
+#: frames of 512 x 512 with every result file written): image_batch 15.7 images/s, 8 threads 53 images/s, 8 processes
+#: 8.8 images/s -- the decoders, numpy and the pickle / PNG writers release the GIL often enough for threads to scale,
+#: while every worker process pays ~15 s of start-up (interpreter, torch import, CUDA context) and processes that share
+#: a GPU time-slice it.  Processes are for one worker per GPU on lists long enough to amortise the start-up.
+PARALLEL_WORKERS = "thread"
+#: seconds after which a worker process that has not answered is given up (logged; its images are reported missing)
+PARALLEL_TIMEOUT_S = 3600.0
+
+
+def _partition_worker(job):
+    """One partition of parallel_image_batch in a worker process: bind to the partition's GPU, carry the parent's
+    solver switches over (module globals are not inherited by a spawned process) and run image_batch."""
+    dev, paths, params, timestamp_epoch, solver, faithful = job
     import torch
-    from . import engine, sharding
+    from . import pflib
+    torch.cuda.set_device(dev)
+    pflib.SOLVER, pflib.FAITHFUL = solver, faithful
+    return image_batch(paths, find_peptides_parameters=params, timestamp_epoch=timestamp_epoch)
+
+
+def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None, num_processes=None, workers=None):
+    """pflib.py:1000-1111 with one GPU per worker: images are balanced over ``num_processes`` partitions by candidate
+    count exactly like the reference (detection runs once on the first device for the count), each partition runs
+    ``image_batch`` on its own GPU (partition k -> device k mod device_count) -- in its own host thread by default, or in
+    its own worker process as the reference does (``workers="process"`` / psfio.PARALLEL_WORKERS).  No collective; the
+    parent merges the workers' {path: result files} dictionaries (pflib.py:1085-1108)."""
+    import torch
+    from . import engine, sharding, pflib
     logger = logging.getLogger()
     if num_processes == 1 or len(image_paths) == 1:
         return image_batch(image_paths, find_peptides_parameters=find_peptides_parameters, timestamp_epoch=timestamp_epoch)
@@ -268,6 +292,9 @@ def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_e
         timestamp_epoch = _py2_round(time.time())
     if num_processes < 1 or round(num_processes) != num_processes:
         raise ValueError("Number of processes must be an integer >= 1")                  # pflib.py:1059-1060
+    workers = workers or PARALLEL_WORKERS
+    if workers not in ("process", "thread"):
+        raise ValueError("workers must be 'process' or 'thread'")
     image_paths = _unique_abs(image_paths)
     params = dict(find_peptides_parameters or {})
     det_kw = {k: params[k] for k in ('median_filter_size', 'correlation_matrix', 'c_std') if k in params}
@@ -282,25 +309,40 @@ def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_e
         paths.append(p)
     parts = sharding.balance_by_count(counts, int(num_processes))
     ndev = max(1, torch.cuda.device_count())
-    results, errors = [None] * len(parts), []
+    live = [k for k in range(len(parts)) if parts[k]]
+    results = {}
 
-    def work(k):
+    if workers == "process" and len(live) > 1:
+        import multiprocessing
+        ctx = multiprocessing.get_context("spawn")          # the parent holds a CUDA context: fork is not an option
+        jobs = {k: (k % ndev, [paths[i] for i in parts[k]], params, timestamp_epoch, pflib.SOLVER, pflib.FAITHFUL) for k in live}
+        pool = ctx.Pool(processes=len(live))
         try:
-            with torch.cuda.device(k % ndev):
-                results[k] = image_batch([paths[i] for i in parts[k]], find_peptides_parameters=params,
-                                         timestamp_epoch=timestamp_epoch)
-        except Exception as e:                           # a failed partition is logged, the others survive
-            logger.exception(e, exc_info=True)
-            errors.append(e)
+            pending = {k: pool.apply_async(_partition_worker, (jobs[k],)) for k in live}
+            for k, fut in pending.items():
+                try:
+                    results[k] = fut.get(timeout=PARALLEL_TIMEOUT_S)
+                except Exception as e:                       # a failed partition is logged, the others survive
+                    logger.exception(e, exc_info=True)
+        finally:
+            pool.terminate()
+            pool.join()
+    else:
+        def work(k):
+            try:
+                with torch.cuda.device(k % ndev):
+                    results[k] = image_batch([paths[i] for i in parts[k]], find_peptides_parameters=params,
+                                             timestamp_epoch=timestamp_epoch)
+            except Exception as e:
+                logger.exception(e, exc_info=True)
 
-    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(parts)) if parts[k]]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+        threads = [threading.Thread(target=work, args=(k,)) for k in live]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     processed = {}
-    for r in results:
-        if r:
-            for k, v in r.items():
-                processed.setdefault(k, v)
+    for k in live:
+        for key, v in (results.get(k) or {}).items():
+            processed.setdefault(key, v)
     return processed

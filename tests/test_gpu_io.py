@@ -68,10 +68,14 @@ def test_parallel_image_batch_equals_image_batch(tmp_path):
     from fluorosequencingimageanalysis_b200 import pflib
     paths, imgs = _write_frames(tmp_path)
     ser = pflib.image_batch(paths, timestamp_epoch=1461000000)
-    par = pflib.parallel_image_batch(paths, timestamp_epoch=1461000010, num_processes=3)
-    assert sorted(par.keys()) == sorted(ser.keys())
-    for k in ser:
-        _same_psfs(pickle.load(open(ser[k][1], 'rb')), pickle.load(open(par[k][1], 'rb')))
+    # host threads (the default) and worker processes (the reference's multiprocessing.Pool): same files either way
+    for epoch, workers in ((1461000010, "process"), (1461000030, "thread")):
+        par = pflib.parallel_image_batch(paths, timestamp_epoch=epoch, num_processes=3, workers=workers)
+        assert sorted(par.keys()) == sorted(ser.keys()), workers
+        for k in ser:
+            _same_psfs(pickle.load(open(ser[k][1], 'rb')), pickle.load(open(par[k][1], 'rb')))
+    with pytest.raises(ValueError):
+        pflib.parallel_image_batch(paths, num_processes=2, workers="fibre")
     with pytest.raises(ValueError):
         pflib.parallel_image_batch(paths, num_processes=2.5)
     assert pflib.parallel_image_batch(paths[:1], timestamp_epoch=1461000020, num_processes=4).keys() == \
