@@ -101,23 +101,38 @@ def save_psfs_csv(psfs, image_path=None, timestamp_epoch=None, output_path=None)
     return output_path
 
 
+def _stretch_limits(a):
+    """1st and 99.9th percentile of the frame for the 8-bit contrast stretch: order statistics from a histogram for
+    integer camera data (0.7 ms on a 512 x 512 frame where two numpy.percentile calls need 18 ms), numpy.percentile
+    otherwise."""
+    if a.dtype.kind in 'iu' and a.size and int(a.min()) >= 0 and int(a.max()) < (1 << 20):
+        cs = np.cumsum(np.bincount(a.ravel()))
+        n = int(cs[-1])
+        return [float(np.searchsorted(cs, q / 100.0 * (n - 1), side='right')) for q in (1.0, 99.9)]
+    lo, hi = np.percentile(np.asarray(a, dtype=np.float64), [1.0, 99.9])
+    return [float(lo), float(hi)]
+
+
 def save_psfs_png(psfs, image_path=None, timestamp_epoch=None, output_path=None, image=None, square_size=9):
     """Sanity-check picture: the frame, contrast-stretched to 8 bits, with a square around every
-    PSF (the role of pflib.py:749-880; rendering details are not part of any numeric contract)."""
+    PSF (the role of pflib.py:749-880; rendering details are not part of any numeric contract).
+    Written as a palette image (254 greys + the squares' red) at PNG compression level 1: the writer was 85 % of
+    image_batch's host time as a level-6 RGB file (86 ms -> 10 ms per 512 x 512 frame)."""
     from PIL import Image, ImageDraw
     image_path, output_path = _resolve_output(image_path, timestamp_epoch, output_path, '.png')
     if image is None:
         image = np.asarray(Image.open(image_path))
-    a = np.asarray(image, dtype=np.float64)
-    lo, hi = np.percentile(a, 1.0), np.percentile(a, 99.9)
-    g = np.clip((a - lo) / max(hi - lo, 1e-12), 0.0, 1.0)
-    rgb = np.repeat((g * 255.0).astype(np.uint8)[:, :, None], 3, axis=2)
-    im = Image.fromarray(rgb, mode='RGB')
+    image = np.asarray(image)
+    lo, hi = _stretch_limits(image)
+    g = np.clip((image.astype(np.float64) - lo) / max(hi - lo, 1e-12), 0.0, 1.0)
+    im = Image.fromarray((g * 253.0).astype(np.uint8), mode='P')          # grey levels 0 .. 253; 255 = the squares
+    pal = [v for k in range(254) for v in (k * 255 // 253,) * 3] + [0, 0, 0] + [255, 64, 64]
+    im.putpalette(pal)
     dr = ImageDraw.Draw(im)
     r = square_size // 2
     for (h, w) in psfs:
-        dr.rectangle([w - r, h - r, w + r, h + r], outline=(255, 64, 64))
-    im.save(output_path)
+        dr.rectangle([w - r, h - r, w + r, h + r], outline=255)
+    im.save(output_path, compress_level=1)
     return output_path
 
 
@@ -255,8 +270,8 @@ def image_batch(image_paths, find_peptides_parameters=None, timestamp_epoch=None
 #: how parallel_image_batch runs its partitions: "thread" = host threads of this process, one per partition, each bound
 #: to its GPU; "process" = one worker process per partition (multiprocessing, spawn context), the reference's arrangement
 #: (multiprocessing.Pool, pflib.py:1082).  Measured on a B200 box (16 host cores, one GPU, tools/gpu_io_bench.py, 384
-#: frames of 512 x 512 with every result file written): image_batch 15.7 images/s, 8 threads 53 images/s, 8 processes
-#: 8.8 images/s -- the decoders, numpy and the pickle / PNG writers release the GIL often enough for threads to scale,
+#: frames of 512 x 512 with every result file written): image_batch 60 images/s, 8 threads 72 images/s, 8 processes
+#: 8.8 images/s -- what is left per image is Python (CSV rows, dictionaries, pickle), so threads gain little over one,
 #: while every worker process pays ~15 s of start-up (interpreter, torch import, CUDA context) and processes that share
 #: a GPU time-slice it.  Processes are for one worker per GPU on lists long enough to amortise the start-up.
 PARALLEL_WORKERS = "thread"
@@ -298,15 +313,39 @@ def parallel_image_batch(image_paths, find_peptides_parameters=None, timestamp_e
     image_paths = _unique_abs(image_paths)
     params = dict(find_peptides_parameters or {})
     det_kw = {k: params[k] for k in ('median_filter_size', 'correlation_matrix', 'c_std') if k in params}
-    paths, counts = [], []
+    # candidate counts for the balance (pflib.py:1056-1069): detection only, same-shape images in bounded device batches
+    paths, counts, pending = [], [], {}
+
+    def count_group(group):
+        try:
+            nc = engine.detect_batch(np.stack([g[1] for g in group]), **det_kw).n_cand.cpu().numpy()
+            got = [(g[0], int(nc[i])) for i, g in enumerate(group)]
+        except Exception:
+            got = []
+            for g in group:                                  # one by one: only the failing image is lost
+                try:
+                    got.append((g[0], int(engine.detect_batch(g[1], **det_kw).total)))
+                except Exception as e:
+                    logger.exception(e, exc_info=True)
+        for p, c in got:
+            paths.append(p)
+            counts.append(c)
+
     for p in image_paths:
         try:
             _, image = read_image(p)
         except Exception as e:
             logger.exception(e, exc_info=True)
             continue
-        counts.append(int(engine.detect_batch(image, **det_kw).total))
-        paths.append(p)
+        key = (image.shape, image.dtype.str)
+        group = pending.setdefault(key, [])
+        group.append((p, image))
+        if len(group) >= BATCH_MAX_FRAMES or len(group) * image.nbytes >= BATCH_MAX_BYTES:
+            count_group(pending.pop(key))
+    for group in pending.values():
+        count_group(group)
+    order = {p: i for i, p in enumerate(image_paths)}        # keep the caller's order (the balance depends on it)
+    paths, counts = (list(t) for t in zip(*sorted(zip(paths, counts), key=lambda pc: order[pc[0]]))) if paths else ([], [])
     parts = sharding.balance_by_count(counts, int(num_processes))
     ndev = max(1, torch.cuda.device_count())
     live = [k for k in range(len(parts)) if parts[k]]

@@ -29,6 +29,12 @@ def main():
             t0 = time.time()
             out = pflib.parallel_image_batch(paths, timestamp_epoch=1461000200 + 100 * k, num_processes=nproc, workers=workers)
             rows.append(("parallel_image_batch, %d %s workers" % (nproc, workers), time.time() - t0, len(out)))
+        if os.environ.get("FSQ_IO_PROFILE"):
+            import cProfile, pstats
+            pr = cProfile.Profile(); pr.enable()
+            pflib.image_batch(paths[:32], timestamp_epoch=1461000900)
+            pr.disable()
+            pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
         for name, dt, m in rows:
             print("%-46s %3d images %7.2f s  %6.2f images/s" % (name, m, dt, m / dt), flush=True)
         print("(%d GPU(s) visible; %d host cores; worker processes pay their start-up -- interpreter, torch import, CUDA context -- inside the timing)"
