@@ -201,16 +201,48 @@ def _find_peptides_many(images, params):
         raise ValueError("consolidation_radius must be at least 2")
     if fit_type != 'gauss':
         raise NotImplementedError("fit_type='monte_carlo' (pflib.py:117-177) is not part of the CUDA hot path")
+    import torch
     stack = np.stack(images)
-    res = engine.find_peptides_batch(stack, faithful=pflib.FAITHFUL, want_fit_img=True, solver=pflib.SOLVER, **kw)
-    offs = np.concatenate([[0], np.cumsum(res.n_cand[:-1])]).astype(np.int64)
+    F = len(images)
+    res = engine.find_peptides_batch(stack, faithful=pflib.FAITHFUL, want_fit_img=True, solver=pflib.SOLVER, to_host=False, **kw)
+    n = int(res.fit.shape[0])
+    if n == 0:
+        return [{} for _ in images]
+    # R^2 gate / consolidation / re-key for the whole batch on the device, then only the FINAL PSFs -- in the
+    # reference's dictionary order (fsq_pack_psfs) -- come to the host: ~0.5 k records per frame instead of ~5 k
+    # candidates with their model images
+    cons = engine.consolidate_batch(res.cand_hw, res.cand_frame, res.fit, n, F, r2t, rad)
+    if int(cons.flags.item()) & 1:
+        # a re-keyed PSF collides with an existing key somewhere in the batch: the reference raises for THAT image
+        # (pflib.py:518), so the images are consolidated one by one
+        offs = np.concatenate([[0], np.cumsum(res.n_cand.cpu().numpy()[:-1])]).astype(np.int64)
+        cand_hw, fit, fit_img = res.cand_hw.cpu().numpy(), res.fit.cpu().numpy(), res.fit_img.cpu().numpy()
+        out = []
+        for f, image in enumerate(images):
+            sl = slice(offs[f], offs[f + 1])
+            try:
+                out.append(pflib.psfs_from_packed(image, cand_hw[sl], fit[sl], fit_img[sl], r2t, rad))
+            except Exception as e:
+                out.append(e)
+        return out
+    packed = engine.pack_psfs_batch(cons, res.cand_frame, res.fit, n, F)
+    base = packed.base.cpu().numpy()
+    m = int(base[-1])
+    ints = packed.ints[:m].cpu().numpy()                  # (frame, key_h, key_w, candidate index)
+    pfit = packed.fit[:m].cpu().numpy()
+    cidx = packed.ints[:m, 3].long()
+    pimg = res.fit_img[cidx].cpu().numpy().reshape(m, 5, 5)
+    phw = res.cand_hw[cidx].cpu().numpy()
     out = []
     for f, image in enumerate(images):
-        sl = slice(offs[f], offs[f + 1])
-        try:
-            out.append(pflib.psfs_from_packed(image, res.cand_hw[sl], res.fit[sl], res.fit_img[sl], r2t, rad))
-        except Exception as e:                            # e.g. the re-key collision assert of pflib.py:518
-            out.append(e)
+        d = {}
+        for i in range(int(base[f]), int(base[f + 1])):
+            h, w = int(phw[i, 0]), int(phw[i, 1])
+            v = pfit[i]
+            d[(int(ints[i, 1]), int(ints[i, 2]))] = (float(v[0]), float(v[1]), float(v[2]), float(v[3]), float(v[4]), float(v[5]), float(v[6]),
+                                                     image[h - 2:h + 3, w - 2:w + 3].astype(np.int64), pimg[i].copy(),
+                                                     float(v[7]), float(v[8]), float(v[9]))
+        out.append(d)
     return out
 
 
