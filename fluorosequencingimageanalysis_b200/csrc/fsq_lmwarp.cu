@@ -36,6 +36,7 @@
 #include "fsq_chol7.cuh"
 #include <string.h>
 #include <atomic>
+#include <type_traits>
 
 namespace fsq {
 
@@ -70,6 +71,7 @@ struct WarpArgs {
     int cap;                                 // phase 1: park a fit after this many passes (0 = never)
     int drain_grace;                         // phase 1: once the queue is empty, park what is still running after this many ticks (0 = never)
     int resume;                              // phase 2: the work list is strag[0 .. *strag_count)
+    long long resume_lo, resume_hi;          // phase 2 runs only if resume_lo <= *strag_count <= resume_hi (else this launch is a no-op)
 };
 
 // Everything the LM kernel needs to start one candidate, written by fit_prep_kernel: a refill is eight
@@ -299,6 +301,55 @@ struct OuterAcc {
     }
 };
 
+#if defined(WPASS_FFMA2) && !defined(WPASS_NO_BASEVEC)
+#define WPASS_BASEVEC 1     // measured on B200: 3.37 -> 3.26 ms per 200-frame launch with three in flight, every parity figure
+                            // unchanged to four digits; 11x11: 6.4 -> 5.1 ms on 200 000 isolated windows
+#endif
+// WPASS_BASEVEC: the pass accumulates the outer products of the BASE vector v = (E, AE a, AE b, AE a^2, AE b^2, AE a b)
+// instead of the Jacobian row j = T v (j1 = -v1, (j2, j3) = R (v2, v3) with R = [[-sx, cyw], [cxw, sy]], j4 = -v4 / wx,
+// j5 = -v5 / wy, j6 = -krot v6): T is the same for every pixel of a pass, so J^T J = T (sum v v^T) T^T, J^T f = T (sum v f)
+// and column 0 follow from the accumulated sums by ~75 multiply-adds per pass, and the eight multiplications per pixel that
+// formed j leave the pixel loop.  S / sg come in as sum v_k v_l, -sum v_k (column 0), sum v_k f and leave as J^T J, J^T f.
+__device__ __forceinline__ void w_basevec_transform(float (&A)[WNT], float (&g)[WNP], const float sx, const float cxw, const float sy,
+                                                    const float cyw, const float iwxf, const float iwyf, const float krot) {
+    const float d4 = -iwxf, d5 = -iwyf, d6 = -krot;
+    // rows 2, 3 of T applied to a pair (p2, p3): (-sx p2 + cyw p3, cxw p2 + sy p3)
+#define W_R2(p2, p3) fmaf(cyw, (p3), -sx * (p2))
+#define W_R3(p2, p3) fmaf(sy, (p3), cxw * (p2))
+    // column 0 and J^T f: the same linear map
+    {
+        const float s10 = A[wtri(1, 0)], s20 = A[wtri(2, 0)], s30 = A[wtri(3, 0)];
+        A[wtri(1, 0)] = -s10; A[wtri(2, 0)] = W_R2(s20, s30); A[wtri(3, 0)] = W_R3(s20, s30);
+        A[wtri(4, 0)] *= d4; A[wtri(5, 0)] *= d5; A[wtri(6, 0)] *= d6;
+        const float g1 = g[1], g2 = g[2], g3 = g[3];
+        g[1] = -g1; g[2] = W_R2(g2, g3); g[3] = W_R3(g2, g3);
+        g[4] *= d4; g[5] *= d5; g[6] *= d6;
+    }
+    const float s21 = A[wtri(2, 1)], s31 = A[wtri(3, 1)], s22 = A[wtri(2, 2)], s32 = A[wtri(3, 2)], s33 = A[wtri(3, 3)];
+    // row / column 1 (d1 = -1)
+    A[wtri(2, 1)] = -W_R2(s21, s31); A[wtri(3, 1)] = -W_R3(s21, s31);
+    A[wtri(4, 1)] *= iwxf; A[wtri(5, 1)] *= iwyf; A[wtri(6, 1)] *= krot;          // d_k d_1 = +1/wx, +1/wy, +krot
+    // the (2, 3) block: R S23 R^T
+    {
+        const float m22 = W_R2(s22, s32), m23 = W_R2(s32, s33);     // row 2 of R S23
+        const float m32 = W_R3(s22, s32), m33 = W_R3(s32, s33);     // row 3 of R S23
+        A[wtri(2, 2)] = W_R2(m22, m23);
+        A[wtri(3, 2)] = W_R2(m32, m33);
+        A[wtri(3, 3)] = W_R3(m32, m33);
+    }
+    // rows 4, 5, 6 against columns 2, 3 and among themselves
+    {
+        const float s42 = A[wtri(4, 2)], s43 = A[wtri(4, 3)], s52 = A[wtri(5, 2)], s53 = A[wtri(5, 3)], s62 = A[wtri(6, 2)], s63 = A[wtri(6, 3)];
+        A[wtri(4, 2)] = d4 * W_R2(s42, s43); A[wtri(4, 3)] = d4 * W_R3(s42, s43);
+        A[wtri(5, 2)] = d5 * W_R2(s52, s53); A[wtri(5, 3)] = d5 * W_R3(s52, s53);
+        A[wtri(6, 2)] = d6 * W_R2(s62, s63); A[wtri(6, 3)] = d6 * W_R3(s62, s63);
+        A[wtri(4, 4)] *= d4 * d4; A[wtri(5, 4)] *= d5 * d4; A[wtri(5, 5)] *= d5 * d5;
+        A[wtri(6, 4)] *= d6 * d4; A[wtri(6, 5)] *= d6 * d5; A[wtri(6, 6)] *= d6 * d6;
+    }
+#undef W_R2
+#undef W_R3
+}
+
 // One pass over the window at pt: chi^2 in FP64; J^T J (packed), J^T f in FP32 (J = d residual / dp).
 //
 // RECUR (the pflib frame path: 5x5 window, widths >= 0.75, centres in [2,3], so every exponent below is
@@ -407,6 +458,10 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
             const float Ef = d2f(E), ff = d2f(f);
             const float AE = Af * Ef;
             const float AEa = AE * af, AEb = AE * bf;
+#if defined(WPASS_FFMA2) && defined(WPASS_BASEVEC)
+            g[0] -= ff;
+            R.add(make_float2(AEa, AEb), make_float2(AEa * af, AEb * bf), make_float2(Ef, AEa * bf), ff);
+#else
             float j[WNP];
             j[1] = -Ef;
             j[2] = AEb * cyw - AEa * sx;                // d/d p[2] (centre along axis 1)
@@ -416,7 +471,9 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
             j[6] = -AEa * bf * krot;                    // degrees
             // column 0 of J is the constant -1
             g[0] -= ff;
-#ifdef WPASS_FFMA2
+#endif
+#if defined(WPASS_FFMA2) && defined(WPASS_BASEVEC)
+#elif defined(WPASS_FFMA2)
             R.add(make_float2(j[2], j[3]), make_float2(j[4], j[5]), make_float2(j[1], j[6]), ff);
 #else
 #pragma unroll
@@ -431,6 +488,9 @@ __device__ __forceinline__ void w_pass(const double (&pt)[WNP], const PXT* __res
     }
 #ifdef WPASS_FFMA2
     R.unpack(A, g);
+#ifdef WPASS_BASEVEC
+    w_basevec_transform(A, g, sx, cxw, sy, cyw, iwxf, iwyf, krot);
+#endif
 #endif
     A[0] = (float)(WIN * WIN);
     ss_out = ss;
@@ -494,6 +554,10 @@ __device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __res
         const float Ef = d2f(E), ff = d2f(f);
         const float AE = Af * Ef;
         const float AEa = AE * af, AEb = AE * bf;
+#if defined(WPASS_FFMA2) && defined(WPASS_BASEVEC)
+        g[0] -= ff;
+        R.add(make_float2(AEa, AEb), make_float2(AEa * af, AEb * bf), make_float2(Ef, AEa * bf), ff);
+#else
         float j[WNP];
         j[1] = -Ef;
         j[2] = AEb * cyw - AEa * sx;
@@ -502,7 +566,9 @@ __device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __res
         j[5] = -AEb * bf * iwyf;
         j[6] = -AEa * bf * krot;
         g[0] -= ff;
-#ifdef WPASS_FFMA2
+#endif
+#if defined(WPASS_FFMA2) && defined(WPASS_BASEVEC)
+#elif defined(WPASS_FFMA2)
         R.add(make_float2(j[2], j[3]), make_float2(j[4], j[5]), make_float2(j[1], j[6]), ff);
 #else
 #pragma unroll
@@ -518,6 +584,9 @@ __device__ __forceinline__ void g_pass(const double (&pt)[WNP], const PXT* __res
     }
 #ifdef WPASS_FFMA2
     R.unpack(A, g);
+#ifdef WPASS_BASEVEC
+    w_basevec_transform(A, g, sx, cxw, sy, cyw, iwxf, iwyf, krot);      // (linear: applied to this lane's partial sums)
+#endif
 #endif
     ss_out = ss;
 }
@@ -577,7 +646,11 @@ lmwarp_kernel(const WarpArgs a) {
     const int maxiter = a.o.maxiter;
     long long n_total = a.n;
     if (a.n_dev) { const long long nd = *a.n_dev; n_total = nd < a.n ? nd : a.n; }
-    if (a.resume) { const long long ns = (long long)*a.strag_count; n_total = ns < n_total ? ns : n_total; }
+    if (a.resume) {
+        const long long ns = (long long)*a.strag_count;
+        if (ns < a.resume_lo || ns > a.resume_hi) return;          // another arrangement finishes this batch's parked fits
+        n_total = ns < n_total ? ns : n_total;
+    }
 
     // ---- per-lane fit state
     bool active = false, exhausted = false;
@@ -1112,8 +1185,11 @@ struct WKernel {
 
 // Persistent launch(es): phase 1 (kernel K1) over every fit -- parked after `park_after` passes when that is set --
 // and phase 2 (kernel K2, by default the same) over the parked fits.
-template <typename K1, typename K2 = K1>
-static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st) {
+// (K3, when given: a second finishing kernel.  K2 takes the parked fits when there are at most `k2_max` of them, K3
+//  otherwise -- both are launched, each reads the parked count on the device and the one whose turn it is not returns
+//  at once, so the choice costs no host synchronisation.)
+template <typename K1, typename K2 = K1, typename K3 = void>
+static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, cudaStream_t st, long long k2_max = 0) {
     int per_sm = 1;
     { const int rc = K1::per_sm(&per_sm); if (rc != FSQ_OK) return rc; }
     const int use_per_sm = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
@@ -1138,8 +1214,20 @@ static int launch_warp(WarpArgs& a, int ctas_per_sm, unsigned long long* head, c
         long long blocks2 = park < 0 ? 16 : (long long)sm_count() * per_sm2;
         const long long need2 = (a.n * K2::grp + K2::tpb - 1) / K2::tpb;
         if (need2 < blocks2) blocks2 = need2 < 1 ? 1 : need2;
-        const int rc = K2::launch(a, blocks2, st);
-        if (rc != FSQ_OK) return rc;
+        a.resume_lo = 0; a.resume_hi = 0x7fffffffffffffffLL;
+        if constexpr (!std::is_void<K3>::value) a.resume_hi = k2_max;
+        { const int rc = K2::launch(a, blocks2, st); if (rc != FSQ_OK) return rc; }
+        if constexpr (!std::is_void<K3>::value) {
+            FSQ_CUDA_CHECK(cudaMemsetAsync(head, 0, sizeof(unsigned long long), st));
+            int per_sm3 = 1;
+            { const int rc = K3::per_sm(&per_sm3); if (rc != FSQ_OK) return rc; }
+            long long blocks3 = (long long)sm_count() * per_sm3;
+            const long long need3 = (a.n * K3::grp + K3::tpb - 1) / K3::tpb;
+            if (need3 < blocks3) blocks3 = need3 < 1 ? 1 : need3;
+            a.resume_lo = k2_max + 1; a.resume_hi = 0x7fffffffffffffffLL;
+            const int rc = K3::launch(a, blocks3, st);
+            if (rc != FSQ_OK) return rc;
+        }
     }
     return FSQ_OK;
 }
@@ -1205,7 +1293,16 @@ static int launch_win11(WarpArgs& a, unsigned long long* head, cudaStream_t st) 
         case -3: return launch_warp<KG8>(a, 0, head, st);
         case -4: return launch_warp<KG2>(a, 0, head, st);
         case -5: if (a.o.park_after == 0) a.o.park_after = W11_PARK; return launch_warp<KT, KG4>(a, 0, head, st);
-        default: if (a.o.park_after == 0) a.o.park_after = W11_PARK; return launch_warp<KT, KG8>(a, 0, head, st);
+        case -6: if (a.o.park_after == 0) a.o.park_after = W11_PARK; return launch_warp<KT, KG8>(a, 0, head, st);
+        default: {
+            // 8 lanes per window have the shorter ticks but half the windows per wave: beyond ~1.75 waves of 8-lane
+            // groups (isolated spots park 5 % of 200 000 windows, a dense field 8 %) the 4-lane kernel finishes sooner
+            if (a.o.park_after == 0) a.o.park_after = W11_PARK;
+            int per_sm8 = 1;
+            { const int rc = KG8::per_sm(&per_sm8); if (rc != FSQ_OK) return rc; }
+            const long long wave8 = (long long)sm_count() * per_sm8 * (KG8::tpb / KG8::grp);
+            return launch_warp<KT, KG8, KG4>(a, 0, head, st, wave8 * 7 / 4);
+        }
     }
 }
 

@@ -113,10 +113,11 @@ typedef struct fsq_lm_opts {
                            far fewer warp-ticks are spent on half-empty warps waiting for their last long
                            fit, and one batch's tail runs underneath the other batches' bulk.
                            fsq_gaussfit_batch, 11x11 windows: 0 = a thread-per-window launch whose
-                           fits are parked after park_after passes (default 32) and finished by the kernel with 8
-                           lanes per window (pass split over the lanes, shuffle reductions); -1 = thread per window
-                           only; -2 / -3 / -4 = 4 / 8 / 2 lanes per window for every fit; -5 = thread-per-window launch
-                           + 4-lane finish.  Same algorithm, different summation order in the lane-group passes: fits
+                           fits are parked after park_after passes (default 32) and finished by the kernel with 8 or
+                           with 4 lanes per window (pass split over the lanes, shuffle reductions; which of the two
+                           depends on the number of parked fits and is decided on the device); -1 = thread per window
+                           only; -2 / -3 / -4 = 4 / 8 / 2 lanes per window for every fit; -5 / -6 = thread-per-window
+                           launch + 4- / 8-lane finish.  Same algorithm, different summation order in the lane-group passes: fits
                            that end before they are parked are bit-identical in every arrangement.          */
 } fsq_lm_opts;
 

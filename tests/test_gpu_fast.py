@@ -353,9 +353,9 @@ def test_config3_experiment_stack_is_frame_independent():
 
 def test_fast_11x11_lane_group_kernels_match_the_reference_too():
     """The arrangements of the 11x11 FAST kernel (fsq_lm_opts.warps_per_sm): 0 = the default, a thread-per-window bulk whose
-    fits are parked after 32 passes and finished by the 8-lanes-per-window kernel; -1 = thread per window only; -2 / -3 /
-    -4 = 4 / 8 / 2 lanes per window for every fit (pass split over the lanes, xor-butterfly sums); -5 = bulk + 4-lane
-    finish.  Same algorithm, different summation order in the lane-group passes: the same figures against the reference
+    fits are parked after 32 passes and finished by the 8- or the 4-lanes-per-window kernel (by the number of parked
+    fits, decided on the device); -1 = thread per window only; -2 / -3 / -4 = 4 / 8 / 2 lanes per window for every fit
+    (pass split over the lanes, xor-butterfly sums); -5 / -6 = bulk + 4- / 8-lane finish.  Same algorithm, different summation order in the lane-group passes: the same figures against the reference
     on both 11x11 golden sets, the same answer as the thread-per-window kernel wherever the fit is not chaotic, and --
     default arrangement -- bit-identical results for every fit that ends before it would be parked."""
     engine, _, _, _lib = _mods()
@@ -365,12 +365,12 @@ def test_fast_11x11_lane_group_kernels_match_the_reference_too():
         lo, hi, lmin, lmax = engine.GAUSSFIT_DEFAULT_LIMITS
         t = lambda v: np.tile(v, (n, 1))
         out = {}
-        for tag, wps in (("thread", -1), ("default", 0), ("g4", -2), ("g8", -3), ("g2", -4), ("bulk+g4", -5)):
+        for tag, wps in (("thread", -1), ("default", 0), ("g4", -2), ("g8", -3), ("g2", -4), ("bulk+g4", -5), ("bulk+g8", -6)):
             o = _lib.default_opts(faithful=False, solver="fast", warps_per_sm=wps)
             r = engine.gaussfit_batch(g["windows"], g["p0"], t(lo), t(hi), t(lmin), t(lmax), solver="fast", opts=o, rescue=False)
             out[tag] = (r.params.cpu().numpy(), r.status.cpu().numpy(), r.chi2.cpu().numpy(), r.nfev.cpu().numpy())
         robust = g["n_qrsolv"] == 0
-        for tag in ("default", "g4", "g8", "g2", "bulk+g4"):
+        for tag in ("default", "g4", "g8", "g2", "bulk+g4", "bulk+g8"):
             P, s, chi, nfev = out[tag]
             ok = agree(P, g["ref_params"]) & (s > 0) & (g["ref_status"] > 0)
             same = agree(P, out["thread"][0])

@@ -1,6 +1,6 @@
 """Developer diagnostic (GPU): the arrangements of the 11x11 FAST kernel (fsq_lm_opts.warps_per_sm: 0 = thread-per-window
-bulk + lane-group finish of the parked fits, -1 thread per window only, -2 / -3 / -4 = 4 / 8 / 2 lanes per window for every
-fit, -5 = bulk + 8-lane finish) on isolated-spot windows (configs[0]) and on windows cut from the dense 2048x2048 frame
+bulk + lane-group finish of the parked fits (8 or 4 lanes per window by their number), -1 thread per window only, -2 / -3 / -4 =
+4 / 8 / 2 lanes per window for every fit, -5 / -6 = bulk + 4- / 8-lane finish) on isolated-spot windows (configs[0]) and on windows cut from the dense 2048x2048 frame
 (configs[3]), with float64 and uint16 window data: time, and results against the thread-per-window kernel.
     python tools/gpu_fit11_variants.py [n_windows] [park_after ...]"""
 import os, sys
@@ -11,7 +11,7 @@ import numpy as np, torch
 from fluorosequencingimageanalysis_b200 import engine, synth, _lib
 from test_gpu_fit import agree
 
-VARIANTS = {"thread": -1, "hybrid8": 0, "hybrid4": -5, "g4": -2, "g8": -3, "g2": -4}
+VARIANTS = {"thread": -1, "hybrid": 0, "hybrid8": -6, "hybrid4": -5, "g4": -2, "g8": -3, "g2": -4}
 
 
 def windows(kind, n):
