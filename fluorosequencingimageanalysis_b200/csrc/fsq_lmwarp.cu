@@ -1320,6 +1320,25 @@ int warp_gaussfit_batch(const void* windows, int dtype_code, long long n, int wi
     fsq_lm_opts o = *opts;
     a.o = o;
     const bool need_strag = (o.park_after != 0) || (win == 11);
+    // The parked-state scratch (128 B per fit: 26 MB for 200 000 windows) comes from the device's stream-ordered pool.
+    // With the pool's default release threshold of 0 the memory goes back to the driver at every synchronisation and
+    // each call pays for a fresh allocation (measured: a 7 ms call became 35 ms inside bench.py); the threshold is
+    // raised once per device so that the pool keeps what it has been given.
+    {
+        static std::atomic<unsigned long long> pool_done{0};
+        int dev = 0;
+        FSQ_CUDA_CHECK(cudaGetDevice(&dev));
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (!(pool_done.load(std::memory_order_acquire) & bit)) {
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            pool_done.fetch_or(bit, std::memory_order_acq_rel);
+        }
+    }
     void* scratch = nullptr;
     const size_t bytes = 64 + (need_strag ? sizeof(StragRec) * (size_t)n : 0);
     FSQ_CUDA_CHECK(cudaMallocAsync(&scratch, bytes, st));
