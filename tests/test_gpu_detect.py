@@ -83,6 +83,23 @@ def test_edge_shapes(shape):
     assert np.array_equal(_cands(det), want)
 
 
+@pytest.mark.parametrize("shape", [(96, 192), (96, 196), (96, 198), (104, 264), (72, 136)])
+def test_interior_tile_staging_paths(shape):
+    """Interior raw tiles are staged three ways by the packed pass-A kernel, chosen per tile: bulk-async row copies (frame
+    base 16-byte aligned, W a multiple of 8), 64-bit loads (W a multiple of 4), reflected index-by-index loads (anything
+    else and every border tile).  Widths 192 / 196 / 198 take one path each in frames that have interior tiles."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    imgs = rng.integers(300, 5000, (3,) + shape).astype(np.uint16)
+    det = _engine().detect_batch(imgs)
+    want = [_want(im) for im in imgs]
+    got = _cands(det)
+    off = 0
+    for w in want:
+        assert np.array_equal(got[off:off + len(w)], w)
+        off += len(w)
+    assert off == det.total
+
+
 def test_flat_and_zero_frames():
     """std == 0: threshold == mean(cm) == 0, every interior pixel is kept (NOT '<', pflib.py:254)."""
     for v in (0, 400):
