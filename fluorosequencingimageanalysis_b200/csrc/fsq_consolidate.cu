@@ -44,6 +44,8 @@ struct ConsScratch {
     int* frame_over;           // [F] frame holds a candidate / component beyond CONS_MAXDEG / CONS_MAXCOMP
     ConsHdr* hdr;              // [n]
     ConsVal* val;              // [n]
+    int* heads;                // [n] accepted candidates without an earlier rival: the only ones that can be the first
+                               //     member of a component (cons_adj appends them in any order; m_total[1] = their number)
 };
 
 static inline long long cons_align(long long x) { return (x + 255) & ~255LL; }
@@ -61,6 +63,7 @@ static long long cons_carve(ConsScratch* s, char* base, long long n, int F) {
     p = take(((long long)F + 1) * 4);      if (s) s->frame_over = (int*)p;
     p = take(n * (long long)sizeof(ConsHdr)); if (s) s->hdr = (ConsHdr*)p;
     p = take(n * (long long)sizeof(ConsVal)); if (s) s->val = (ConsVal*)p;
+    p = take(n * 4);                       if (s) s->heads = (int*)p;
     return off;
 }
 
@@ -110,7 +113,7 @@ cons_scan_kernel(int* __restrict__ blockcount, long long nb, long long* __restri
         if (tid == 1023) carry += buf[1023];
         __syncthreads();
     }
-    if (tid == 0) *m_total = carry;
+    if (tid == 0) { m_total[0] = carry; m_total[1] = 0; }      // [1]: length of the component-head list (cons_adj_kernel appends)
 }
 
 __global__ void __launch_bounds__(256)
@@ -177,7 +180,7 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
         if (!last_in) break;
     }
     int deg = 0;
-    bool over = false;
+    bool over = false, earlier = false;
     short* adj = s.adj + a * CONS_MAXDEG;
     for (long long base = lo; base < m; base += CONS_BATCH) {
         ConsHdr hj[CONS_BATCH];
@@ -193,6 +196,7 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
                 const ConsVal vj = s.val[j];
                 if (!cons_far(va, vj, rr)) {
                     const long long off = j - a;
+                    earlier |= (off < 0);
                     if (deg < CONS_MAXDEG && off >= -32768 && off <= 32767) adj[deg] = (short)off;
                     else over = true;
                     ++deg;
@@ -205,6 +209,10 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
     // publishes NO rival list: a partly written list must never be walked (the scratch is uninitialised memory)
     if (over) { atomicOr(&s.frame_over[ha.f], 1); deg = 0; }
     s.deg[a] = (unsigned char)deg;
+    // a candidate with an earlier rival cannot be the first member of its component: only the others start a walk in
+    // cons_component_kernel, packed (one walk per lane instead of one per ~4 lanes).  The order of the list does not
+    // matter -- components are independent.  (The compiler aggregates the atomic over the warp.)
+    if (!earlier && !over) s.heads[atomicAdd(reinterpret_cast<unsigned long long*>(s.m_total + 1), 1ull)] = (int)a;
 }
 
 // one walk per accepted candidate; only the first member of a component completes it and replays pflib.py:479-512
@@ -212,9 +220,10 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
 //  measured: 70 us instead of 58 us per 40-frame batch -- the local arrays cost more than the loads they save.)
 __global__ void __launch_bounds__(128)
 cons_component_kernel(ConsScratch s) {
-    const long long m = *s.m_total;
-    const long long a = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (a >= m) return;
+    const long long nh = s.m_total[1];
+    const long long hpos = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (hpos >= nh) return;
+    const long long a = s.heads[hpos];
     if (s.frame_over[s.hdr[a].f]) return;                      // the whole frame is redone by cons_fallback_kernel
     int member[CONS_MAXCOMP];
     int cnt = 1;
