@@ -113,7 +113,9 @@ cons_scan_kernel(int* __restrict__ blockcount, long long nb, long long* __restri
         if (tid == 1023) carry += buf[1023];
         __syncthreads();
     }
-    if (tid == 0) { m_total[0] = carry; m_total[1] = 0; }      // [1]: length of the component-head list (cons_adj_kernel appends)
+    if (tid == 0) { m_total[0] = carry; m_total[1] = 0; m_total[2] = 0; }   // [1]: length of the component-head list (cons_adj_kernel
+                                                                           // appends); [2]: "some accepted fit has its centre more than
+                                                                           // half a pixel from its candidate pixel" (cons_scatter_kernel)
 }
 
 __global__ void __launch_bounds__(256)
@@ -136,6 +138,9 @@ cons_scatter_kernel(const double* __restrict__ fit, long long n, const long long
         hd.f = cand_frame[i]; hd.h = cand_hw[2 * i]; hd.w = cand_hw[2 * i + 1]; hd.idx = (int)i;
         ConsVal v;
         v.h0 = fit[i * 12 + 0]; v.w0 = fit[i * 12 + 1]; v.r2 = fit[i * 12 + 8];
+        // pflib fits keep their centre within half a pixel of the candidate pixel (centre limits [2, 3] in the 5x5 window);
+        // anything else (NaN included) makes cons_finish_kernel run the collision check of pflib.py:518 -- see there
+        if (!(fabs(v.h0 - (double)hd.h) <= 0.5 && fabs(v.w0 - (double)hd.w) <= 0.5)) s.m_total[2] = 1;
         *reinterpret_cast<int4*>(&s.hdr[pos]) = *reinterpret_cast<const int4*>(&hd);
         s.val[pos] = v;
         s.alive[pos] = 1;
@@ -317,10 +322,14 @@ cons_finish_kernel(ConsScratch s, int reach, unsigned char* __restrict__ psf_sta
         const unsigned peers = __match_any_sync(__activemask(), ha.f);
         if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&n_psf[ha.f], (unsigned long long)__popc(peers));
     }
-    if (moved) {
+    if (moved && s.m_total[2] != 0) {
         // :518 asserts that the new key is free at the moment of the move: earlier survivors sit at their FINAL
-        // keys by then, later ones still at their candidate pixels.  (Cannot happen when the fitted centre lies
-        // within 0.5 px of the candidate pixel, as it does for pflib fits; checked within the rival reach.)
+        // keys by then, later ones still at their candidate pixels.  The scan is skipped when EVERY accepted fit of the
+        // batch has its centre within half a pixel of its candidate pixel on both axes (m_total[2] == 0, the case for pflib
+        // fits): two survivors that end on one key then have centres within one pixel per axis of each other
+        // (<= 1.42 px <= the radius, which is at least 2) and candidate pixels within two (<= radius + 2, the window), i.e.
+        // they are rivals -- and of two rivals the consolidation never leaves both alive.  Otherwise: checked within the
+        // rival reach.
         long long b = a;
         while (b > 0 && s.hdr[b - 1].f == ha.f && s.hdr[b - 1].h >= kh - reach - 1) --b;
         bool stop = false;
