@@ -168,6 +168,10 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
     if (a >= m) return;
     const ConsHdr ha = cons_ld_hdr(s.hdr, a);
     const ConsVal va = s.val[a];
+    // When every accepted centre lies within half a pixel of its candidate pixel (m_total[2] == 0, pflib fits), two
+    // candidates whose pixels are reach = radius + 2 rows apart have centres more than the radius apart: the outermost
+    // window rows cannot hold a rival and are not scanned (13 -> 11 rows at the default radius).
+    const int rreach = (s.m_total[2] == 0 && reach > 1) ? reach - 1 : reach;
     // first accepted position inside the window rows (the list is sorted by frame, row, column)
     long long lo = a;
     for (long long base = a - 1; base >= 0; base -= CONS_BATCH) {
@@ -178,7 +182,7 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
 #pragma unroll
         for (int q = 0; q < CONS_BATCH; ++q) {
             const long long b = base - q;
-            const bool in = (b >= 0) && (hb[q].f == ha.f) && (hb[q].h >= ha.h - reach);
+            const bool in = (b >= 0) && (hb[q].f == ha.f) && (hb[q].h >= ha.h - rreach);
             lo = in ? b : lo;                                  // `in` is monotone along the scan
             last_in = in;
         }
@@ -195,7 +199,7 @@ cons_adj_kernel(ConsScratch s, int reach, double rr) {
 #pragma unroll
         for (int q = 0; q < CONS_BATCH; ++q) {
             const long long j = base + q;
-            const bool in = (j < m) && (hj[q].f == ha.f) && (hj[q].h <= ha.h + reach);
+            const bool in = (j < m) && (hj[q].f == ha.f) && (hj[q].h <= ha.h + rreach);
             last_in = in;
             if (in && j != a && abs(hj[q].w - ha.w) <= reach) {
                 const ConsVal vj = s.val[j];
